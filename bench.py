@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py - selective-scan tokens/s at L=4096, d_model=2048 (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--seqlen L] [--no-cpu]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (mamba_chunk_scan_combined forward) over one batch of
+65 536 synthetic tokens per GPU: (B, L) = (16, 4096), H=64, P=64, G=1, N=128, bf16 I/O.
+  value      tokens/s, inputs resident in HBM, CUDA events on the launch stream, max over ranks
+  e2e        same call through the public API with pinned HOST buffers: H2D of x/dt/B/C + D2H of y inside the timed region
+  roofline   algorithmic bytes (17 024 B/token fwd) / measured kernel time vs MEASURED_PEAKS.json hbm_gbs
+  fwd_bwd    tokens/s of forward + backward (42 880 B/token algorithmic), reported beside the headline
+  cpu_baseline  the oracle's fp32 recurrent loop (the reference's "pure-PyTorch recurrent fallback") on the host cores
+The scan is sequence-local: multi-GPU = independent replicas on their own batch shard (no data-path collective);
+the fwd+bwd leg all-reduces the (tiny) parameter gradients over NCCL, as DDP would.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+H, P, G, N = 64, 64, 1, 128
+TOKENS_PER_GPU = 65536
+BYTES_FWD = 2 * (2 * H * P + H + 2 * G * N)                      # 17 024 B/token
+BYTES_FWD_BWD = 42880                                            # fwd 17 024 + bwd (dy 8192 + re-read 8832 + write 8832)
+METRIC = "selective-scan tokens/s (fwd) at L=4k d=2048"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def make_inputs(batch, seqlen, seed=0):
+    """SURVEY.md 8(d) synthetic inputs on the HOST: x, B, C, raw dt ~ N(0,1) bf16; Mamba2-init dt_bias; A = -U(1,16); D = 1."""
+    g = torch.Generator().manual_seed(seed)
+    n = lambda *s: torch.randn(*s, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    x, dt = n(batch, seqlen, H, P), n(batch, seqlen, H)
+    Bm, Cm = n(batch, seqlen, G, N), n(batch, seqlen, G, N)
+    A = -(torch.rand(H, generator=g) * 15 + 1)
+    dt0 = torch.exp(torch.rand(H, generator=g) * (math.log(0.1) - math.log(1e-3)) + math.log(1e-3)).clamp(min=1e-4)
+    dt_bias = dt0 + torch.log(-torch.expm1(-dt0))
+    return dict(x=x, dt=dt, A=A, B=Bm, C=Cm, D=torch.ones(H), dt_bias=dt_bias)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def time_cuda(fn, steps, warmup, dist_on):
+    """W warm-ups, then EXACTLY `steps` calls bracketed by barrier + synchronize; returns seconds (this rank)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+    return e0.elapsed_time(e1) / 1e3
+
+
+def max_over_ranks(v, dist_on, device):
+    if not dist_on:
+        return v
+    t = torch.tensor([v], device=device, dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def cpu_arm(seconds_target=15.0, seqlen=None):
+    """The oracle's fp32 recurrent loop at d_model=2048, B=1, all host threads.  Returns (tokens/s, cores, sample)."""
+    import oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    from cases import scan_inputs
+    probe = 64
+    x, dt, A, Bm, Cm, D, dt_bias = scan_inputs(1, probe, H, P, G, N, 0, torch.float32)
+    t0 = time.perf_counter()
+    oracle.cpu_recurrent_baseline(x, dt, A, Bm, Cm, D, dt_bias)
+    per_tok = (time.perf_counter() - t0) / probe
+    if seqlen is None:
+        seqlen = int(max(128, min(4096, seconds_target / max(per_tok, 1e-9))))
+    x, dt, A, Bm, Cm, D, dt_bias = scan_inputs(1, seqlen, H, P, G, N, 0, torch.float32)
+    t0 = time.perf_counter()
+    oracle.cpu_recurrent_baseline(x, dt, A, Bm, Cm, D, dt_bias)
+    el = time.perf_counter() - t0
+    return seqlen / el, torch.get_num_threads(), f"B=1 L={seqlen} d_model=2048 fp32 recurrent token loop ({el:.1f} s)", seqlen, el
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: mamba_ssm is not installable
+    here) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    seqlen = None
+    times, toks = [], 0
+    per_step = min(8.0, max(0.5, 120.0 / (args.warmup + args.steps)))  # whole run ends within a few minutes
+    for i in range(args.warmup + args.steps):
+        tps, cores, sample, seqlen, el = cpu_arm(seconds_target=per_step, seqlen=seqlen)
+        if i >= args.warmup:
+            times.append(el)
+            toks += seqlen
+    total = sum(times)
+    v = toks / total
+    line = {"metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"mamba_chunk_scan_combined fwd, d_model=2048 (H=64,P=64,G=1,N=128), bounded sample B=1 L={seqlen}",
+                       "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seqlen", type=int, default=4096)
+    ap.add_argument("--algo", default="auto", choices=["auto", "recurrent", "chunked_tc"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-bwd", action="store_true", help="skip the fwd+bwd leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: omnimamba_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=device)
+
+    from omnimamba_b200 import _cabi
+    from omnimamba_b200.interface.ssd_combined import mamba_chunk_scan_combined, ssd_bwd_raw, ssd_fwd_raw
+    _cabi.lib()
+
+    L = args.seqlen
+    batch = max(1, TOKENS_PER_GPU // L)
+    tokens = batch * L
+    host = make_inputs(batch, L, seed=rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    dev = {k: v.to(device) for k, v in host.items()}
+    out = torch.empty(batch, L, H, P, device=device, dtype=torch.bfloat16)
+
+    def fwd():
+        ssd_fwd_raw(dev["x"], dev["dt"], dev["A"], dev["B"], dev["C"], 256, D=dev["D"], dt_bias=dev["dt_bias"],
+                    dt_softplus=True, out=out, algo=args.algo)
+
+    # ---- headline: device-resident forward ---------------------------------------------------------------
+    _cabi.reset_launch_count()
+    with ClockSampler(local_rank) as clk:
+        t_fwd = time_cuda(fwd, args.steps, args.warmup, dist_on)
+    launches = _cabi.launch_count() * args.steps // (args.steps + args.warmup)
+    t_fwd = max_over_ranks(t_fwd, dist_on, device)
+    value = world * tokens * args.steps / t_fwd
+    hbm, how = peaks()
+    kernel_s = t_fwd / args.steps  # one kernel launch per step: the step IS the dominant kernel's duration
+    achieved = tokens * BYTES_FWD / kernel_s / 1e9
+
+    # ---- fwd + bwd -----------------------------------------------------------------------------------------
+    fb = None
+    if not args.no_bwd:
+        dy = torch.randn(batch, L, H, P, device=device, dtype=torch.bfloat16)
+
+        def fwd_bwd():
+            fwd()
+            r = ssd_bwd_raw(dy, dev["x"], dev["dt"], dev["A"], dev["B"], dev["C"], 256, D=dev["D"], dt_bias=dev["dt_bias"],
+                            dt_softplus=True, algo=args.algo)
+            if dist_on:  # DDP semantics: only parameter gradients cross NVLink
+                flat = torch.cat([r[2], r[5], r[7]])
+                torch.distributed.all_reduce(flat)
+
+        steps_fb = max(3, args.steps // 4)
+        t_fb = max_over_ranks(time_cuda(fwd_bwd, steps_fb, 3, dist_on), dist_on, device)
+        fb_tps = world * tokens * steps_fb / t_fb
+        fb = {"value": fb_tps, "unit": "tokens/s", "ms_per_step": 1e3 * t_fb / steps_fb,
+              "roofline_frac": (fb_tps / world) * BYTES_FWD_BWD / 1e9 / hbm, "bytes_per_token": BYTES_FWD_BWD}
+        del dy
+
+    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region ------------------------
+    out_host = torch.empty(batch, L, H, P, dtype=torch.bfloat16).pin_memory()
+    big = ("x", "dt", "B", "C")
+    stage = {k: torch.empty_like(dev[k]) for k in big}
+
+    def e2e_step():
+        for k in big:
+            stage[k].copy_(pinned[k], non_blocking=True)
+        y = mamba_chunk_scan_combined(stage["x"], stage["dt"], dev["A"], stage["B"], stage["C"], 256, D=dev["D"],
+                                      dt_bias=dev["dt_bias"], dt_softplus=True)
+        out_host.copy_(y, non_blocking=True)
+
+    steps_e = max(3, min(args.steps, 10))
+    with torch.no_grad():
+        t_e = max_over_ranks(time_cuda(e2e_step, steps_e, 3, dist_on), dist_on, device)
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in big)
+    d2h = out_host.numel() * out_host.element_size()
+    e2e = {"value": world * tokens * steps_e / t_e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        tps, cores, sample, _, _ = cpu_arm()
+        cpu = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_fwd / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 io / f32 state", "data": "synthetic",
+            "config": {"workload": f"mamba_chunk_scan_combined fwd: B={batch} L={L} H={H} P={P} G={G} N={N} (d_model=2048), "
+                                   f"D, dt_bias, dt_softplus, z=None; {tokens} tokens/GPU/step",
+                       "algo": args.algo, "parallelism": f"replicas x{world} (batch-sharded, no data-path collective)",
+                       "l2": f"inputs+output {tokens * BYTES_FWD / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": None, "peak_source": f"{how} (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback",
+                         "bytes_per_token": BYTES_FWD, "kernel": "ssd forward (one launch per step)"},
+            "fwd_bwd": fb, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

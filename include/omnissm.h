@@ -1,0 +1,228 @@
+/*
+ * omnissm.h - C ABI of libomnissm.so: the B200 (sm_100a) kernels behind the
+ * mamba_ssm / causal_conv1d operator surface that hustvl/OmniMamba reaches from
+ * models/stage2/mixer_seq_simple.py:15-20,30 and models/stage2/block.py:10,86-95,117.
+ *
+ * Conventions:
+ *   - plain C: POD structs, raw device pointers, element strides; no torch types.
+ *   - the caller owns ALL memory (inputs, outputs, workspaces); the library never
+ *     allocates, frees or retains device memory and never synchronises the host.
+ *   - every entry point launches on the caller-supplied stream (a cudaStream_t passed
+ *     as void*), is re-entrant, and is CUDA-graph capturable.
+ *   - return 0 on success, an omni_status_t otherwise; omni_last_error() gives the
+ *     thread-local message.  No exceptions cross the boundary.
+ *   - a tensor argument whose .data is NULL is "absent" (the Python None).
+ *
+ * Each entry point cites the reference-side Python interface it replaces; the
+ * upstream wheels pinned by /root/reference/requirements.txt:12-13 bind the same
+ * operations through pybind modules (selective_scan_cuda, causal_conv1d_cuda) and
+ * Triton JIT kernels.
+ */
+#ifndef OMNISSM_H_
+#define OMNISSM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMNI_ABI_VERSION 1
+#if defined(__GNUC__)
+#define OMNI_API __attribute__((visibility("default")))
+#else
+#define OMNI_API
+#endif
+#define OMNI_MAX_DIMS 6
+
+typedef enum {
+  OMNI_OK = 0,
+  OMNI_BAD_SHAPE = 1,
+  OMNI_BAD_DTYPE = 2,
+  OMNI_BAD_STRIDE = 3,
+  OMNI_UNSUPPORTED = 4,
+  OMNI_CUDA_ERROR = 5
+} omni_status_t;
+
+typedef enum { OMNI_F32 = 0, OMNI_F16 = 1, OMNI_BF16 = 2, OMNI_I32 = 3, OMNI_I64 = 4 } omni_dtype_t;
+
+typedef enum { OMNI_ACT_NONE = 0, OMNI_ACT_SILU = 1 } omni_activation_t;
+
+/* Strided view of device memory. Strides are in ELEMENTS and may be 0 (broadcast). */
+typedef struct omni_tensor {
+  void* data;
+  int32_t dtype; /* omni_dtype_t */
+  int32_t ndim;
+  int64_t shape[OMNI_MAX_DIMS];
+  int64_t stride[OMNI_MAX_DIMS];
+} omni_tensor_t;
+
+/* SSD algorithm selector (omni_ssd_params_t.algo). AUTO picks the tcgen05 chunked kernel when the
+ * shape/dtype allows and the exact SIMT recurrence otherwise. */
+typedef enum { OMNI_SSD_AUTO = 0, OMNI_SSD_RECURRENT = 1, OMNI_SSD_CHUNKED_TC = 2 } omni_ssd_algo_t;
+
+/* ---- library ---------------------------------------------------------------------------- */
+OMNI_API int omni_version(void);
+OMNI_API const char* omni_last_error(void);
+/* Comma-separated names of the device kernels this library has launched in this process
+ * (evidence for "which native code ran"); the count is cumulative. */
+OMNI_API int64_t omni_launch_count(void);
+OMNI_API void omni_reset_launch_count(void);
+
+/* ---- causal depthwise conv1d ------------------------------------------------------------- */
+/* causal_conv1d_fn(x, weight, bias, seq_idx, initial_states, return_final_states, final_states_out,
+ * activation)  [causal_conv1d/causal_conv1d_interface.py; Mamba2.forward paths A/B, SURVEY.md 3.2].
+ *   x, out: (B, D, L) any strides (channel-last stride(1)==1 is the fast path);
+ *   weight: (D, W) 2<=W<=4; bias: (D) or absent; seq_idx: (B, L) int32 or absent;
+ *   initial_states / final_states: (B, D, W-1) or absent. */
+typedef struct omni_conv1d_fwd_params {
+  omni_tensor_t x, weight, bias, seq_idx, initial_states;
+  omni_tensor_t out, final_states;
+  int32_t activation; /* omni_activation_t */
+} omni_conv1d_fwd_params_t;
+OMNI_API int omni_causal_conv1d_fwd(const omni_conv1d_fwd_params_t* p, void* stream);
+
+/* Backward of the above (causal_conv1d_cuda.causal_conv1d_bwd upstream).
+ *   dweight (D, W) and dbias (D) are FP32 and must be ZEROED by the caller (accumulated with
+ *   atomics); dx like x; dinitial_states (B, D, W-1) optional. */
+typedef struct omni_conv1d_bwd_params {
+  omni_tensor_t x, weight, bias, dout, seq_idx, initial_states;
+  omni_tensor_t dx, dweight, dbias, dinitial_states;
+  int32_t activation;
+} omni_conv1d_bwd_params_t;
+OMNI_API int omni_causal_conv1d_bwd(const omni_conv1d_bwd_params_t* p, void* stream);
+
+/* causal_conv1d_update(x, conv_state, weight, bias, activation, cache_seqlens)
+ * [Mamba2.step, SURVEY.md 3.2 path C].  x/out: (B, D, T); conv_state: (B, D, S>=W-1) mutated in place;
+ * cache_seqlens: (B) int32 or absent (ring-buffer mode). */
+typedef struct omni_conv1d_update_params {
+  omni_tensor_t x, conv_state, weight, bias, cache_seqlens;
+  omni_tensor_t out;
+  int32_t activation;
+} omni_conv1d_update_params_t;
+OMNI_API int omni_causal_conv1d_update(const omni_conv1d_update_params_t* p, void* stream);
+
+/* ---- SSD chunked scan (Mamba-2) ---------------------------------------------------------- */
+/* mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size, D, z, dt_bias, initial_states, seq_idx,
+ * dt_softplus, dt_limit, return_final_states)  [mamba_ssm/ops/triton/ssd_combined.py; SURVEY.md 8(a) a4].
+ *   x, z, out: (B, L, H, P); dt: (B, L, H); A: (H) fp32; B, C: (B, L, G, N);
+ *   D: (H) or (H, P); dt_bias: (H); initial_states / final_states: (B, H, P, N) (final: fp32);
+ *   seq_idx: (B, L) int32.  Innermost dims of x/z/out/B/C must be contiguous. */
+typedef struct omni_ssd_fwd_params {
+  omni_tensor_t x, dt, A, B, C, D, z, dt_bias, initial_states, seq_idx;
+  omni_tensor_t out, final_states;
+  int32_t chunk_size; /* accepted for API parity; the result does not depend on it */
+  int32_t dt_softplus;
+  float dt_min, dt_max; /* dt_limit */
+  int32_t algo;         /* omni_ssd_algo_t */
+} omni_ssd_fwd_params_t;
+OMNI_API int omni_ssd_chunk_scan_fwd(const omni_ssd_fwd_params_t* p, void* stream);
+
+/* Backward.  dout like out.  Outputs: dx like x; ddt (B, L, H) in dt's dtype (gradient w.r.t. the RAW dt);
+ * dB, dC: (B, L, G, N) FP32, ZEROED by the caller; dz like z (optional); dinitial_states (B,H,P,N) fp32
+ * optional; per-(batch, head) FP32 partials the caller sums over batch: dA_part, ddt_bias_part: (B, H),
+ * dD_part: (B, H) or (B, H, P).  dfinal_states (B,H,P,N) optional incoming gradient.
+ * workspace: FP32, omni_ssd_bwd_workspace_elems() elements. */
+typedef struct omni_ssd_bwd_params {
+  omni_tensor_t x, dt, A, B, C, D, z, dt_bias, initial_states, seq_idx;
+  omni_tensor_t dout, dfinal_states;
+  omni_tensor_t dx, ddt, dB, dC, dz, dinitial_states, dA_part, ddt_bias_part, dD_part;
+  omni_tensor_t workspace;
+  int32_t chunk_size;
+  int32_t dt_softplus;
+  float dt_min, dt_max;
+  int32_t algo;
+} omni_ssd_bwd_params_t;
+OMNI_API int64_t omni_ssd_bwd_workspace_elems(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim,
+                                     int64_t dstate);
+OMNI_API int omni_ssd_chunk_scan_bwd(const omni_ssd_bwd_params_t* p, void* stream);
+
+/* ---- gated RMSNorm / LayerNorm ------------------------------------------------------------ */
+/* rmsnorm_fn / layernorm_fn(x, weight, bias, z, eps, group_size, norm_before_gate)
+ * [mamba_ssm/ops/triton/layernorm_gated.py; SURVEY.md A.4].  x, z, out: (M, D) row-major (row stride
+ * free); weight/bias: (D); rstd/mean: (M, D/group_size) fp32 outputs (mean only for LayerNorm). */
+typedef struct omni_norm_gated_fwd_params {
+  omni_tensor_t x, weight, bias, z;
+  omni_tensor_t out, rstd, mean;
+  float eps;
+  int32_t group_size;
+  int32_t norm_before_gate;
+  int32_t is_rms_norm;
+} omni_norm_gated_fwd_params_t;
+OMNI_API int omni_norm_gated_fwd(const omni_norm_gated_fwd_params_t* p, void* stream);
+
+/* Backward: dx, dz like x; dw_part/db_part: (nparts, D) fp32 partial sums (caller sums over dim 0;
+ * nparts = dw_part.shape[0] chosen by the caller, typically the SM count); out_recompute optional
+ * (re-materialised forward output, used for the out_proj weight gradient). */
+typedef struct omni_norm_gated_bwd_params {
+  omni_tensor_t x, weight, bias, z, dout, rstd, mean;
+  omni_tensor_t dx, dz, dw_part, db_part, out_recompute;
+  float eps;
+  int32_t group_size;
+  int32_t norm_before_gate;
+  int32_t is_rms_norm;
+} omni_norm_gated_bwd_params_t;
+OMNI_API int omni_norm_gated_bwd(const omni_norm_gated_bwd_params_t* p, void* stream);
+
+/* ---- fused residual-add + norm ------------------------------------------------------------ */
+/* layer_norm_fn(x, weight, bias, residual, eps, prenorm, residual_in_fp32, is_rms_norm)
+ * [mamba_ssm/ops/triton/layer_norm.py; call sites block.py:86-95, mixer_seq_simple.py:428-437].
+ *   x: (M, D); residual: (M, D) or absent; y: (M, D) in x's dtype... see omnimamba_b200/interface;
+ *   residual_out: (M, D) (absent => not written); rstd/mean: (M) fp32. */
+typedef struct omni_add_norm_fwd_params {
+  omni_tensor_t x, residual, weight, bias;
+  omni_tensor_t y, residual_out, rstd, mean;
+  float eps;
+  int32_t is_rms_norm;
+} omni_add_norm_fwd_params_t;
+OMNI_API int omni_add_norm_fwd(const omni_add_norm_fwd_params_t* p, void* stream);
+
+/* Backward.  xres is the saved normalised-input (= residual_out, or x when there was no add);
+ * dy: (M, D); dresidual_in: optional incoming gradient of residual_out (prenorm);
+ * dx: (M, D) (also the gradient of the incoming residual - same values); dw_part/db_part as above. */
+typedef struct omni_add_norm_bwd_params {
+  omni_tensor_t xres, weight, bias, dy, dresidual_in, rstd, mean;
+  omni_tensor_t dx, dresidual, dw_part, db_part; /* dresidual: optional copy of dx in the residual's dtype */
+  float eps;
+  int32_t is_rms_norm;
+} omni_add_norm_bwd_params_t;
+OMNI_API int omni_add_norm_bwd(const omni_add_norm_bwd_params_t* p, void* stream);
+
+/* ---- single-token recurrent update -------------------------------------------------------- */
+/* selective_state_update(state, x, dt, A, B, C, D, z, dt_bias, dt_softplus)
+ * [mamba_ssm/ops/triton/selective_state_update.py; Mamba2.step; scripts/inference_t2i.py decode loop via
+ * models/stage2/generation.py:208-211].  Head form: state (B,H,P,N) mutated in place; x, dt, z, out:
+ * (B,H,P); A: (H,P,N); B, C: (B,G,N); D, dt_bias: (H,P).  Stride-0 broadcasts are expected. */
+typedef struct omni_ssu_params {
+  omni_tensor_t state, x, dt, A, B, C, D, z, dt_bias;
+  omni_tensor_t out;
+  int32_t dt_softplus;
+} omni_ssu_params_t;
+OMNI_API int omni_selective_state_update(const omni_ssu_params_t* p, void* stream);
+
+/* ---- Mamba-1 selective scan ---------------------------------------------------------------- */
+/* selective_scan_fn(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+ * [mamba_ssm/ops/selective_scan_interface.py; reachable via ssm_cfg.layer="Mamba1",
+ * mixer_seq_simple.py:197-201].  u, delta, z, out: (B, D, L); A: (D, N) fp32; B, C: (B, G, N, L);
+ * D, delta_bias: (D) fp32; last_state: (B, D, N) fp32 optional. */
+typedef struct omni_selscan_fwd_params {
+  omni_tensor_t u, delta, A, B, C, D, z, delta_bias;
+  omni_tensor_t out, last_state;
+  int32_t delta_softplus;
+} omni_selscan_fwd_params_t;
+OMNI_API int omni_selective_scan_fwd(const omni_selscan_fwd_params_t* p, void* stream);
+
+/* Backward: du, ddelta like u; dB, dC (B, G, N, L) FP32 zeroed by caller; dz optional;
+ * dA_part (B, D, N), dD_part, ddelta_bias_part (B, D) fp32 partials; workspace fp32 (B*D*L). */
+typedef struct omni_selscan_bwd_params {
+  omni_tensor_t u, delta, A, B, C, D, z, delta_bias, dout;
+  omni_tensor_t du, ddelta, dB, dC, dz, dA_part, dD_part, ddelta_bias_part, workspace;
+  int32_t delta_softplus;
+} omni_selscan_bwd_params_t;
+OMNI_API int omni_selective_scan_bwd(const omni_selscan_bwd_params_t* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMNISSM_H_ */

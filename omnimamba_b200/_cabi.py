@@ -1,0 +1,193 @@
+"""ctypes binding of libomnissm.so (include/omnissm.h).
+
+The structures here mirror the header field-for-field.  There is NO fallback: if the shared
+library is missing (or a tensor is not on a CUDA device) the call raises - the product path
+never routes through the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+OMNI_MAX_DIMS = 6
+OMNI_F32, OMNI_F16, OMNI_BF16, OMNI_I32, OMNI_I64 = 0, 1, 2, 3, 4
+ACT_NONE, ACT_SILU = 0, 1
+SSD_AUTO, SSD_RECURRENT, SSD_CHUNKED_TC = 0, 1, 2
+
+_DTYPES = {
+    torch.float32: OMNI_F32, torch.float16: OMNI_F16, torch.bfloat16: OMNI_BF16,
+    torch.int32: OMNI_I32, torch.int64: OMNI_I64,
+}
+
+_STATUS = {1: "BAD_SHAPE", 2: "BAD_DTYPE", 3: "BAD_STRIDE", 4: "UNSUPPORTED", 5: "CUDA_ERROR"}
+
+
+class Tensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("dtype", C.c_int32), ("ndim", C.c_int32),
+                ("shape", C.c_int64 * OMNI_MAX_DIMS), ("stride", C.c_int64 * OMNI_MAX_DIMS)]
+
+
+def _T(*names):
+    return [(n, Tensor) for n in names]
+
+
+class Conv1dFwd(C.Structure):
+    _fields_ = _T("x", "weight", "bias", "seq_idx", "initial_states", "out", "final_states") + [("activation", C.c_int32)]
+
+
+class Conv1dBwd(C.Structure):
+    _fields_ = _T("x", "weight", "bias", "dout", "seq_idx", "initial_states", "dx", "dweight", "dbias",
+                  "dinitial_states") + [("activation", C.c_int32)]
+
+
+class Conv1dUpdate(C.Structure):
+    _fields_ = _T("x", "conv_state", "weight", "bias", "cache_seqlens", "out") + [("activation", C.c_int32)]
+
+
+class SsdFwd(C.Structure):
+    _fields_ = _T("x", "dt", "A", "B", "C", "D", "z", "dt_bias", "initial_states", "seq_idx", "out", "final_states") + [
+        ("chunk_size", C.c_int32), ("dt_softplus", C.c_int32), ("dt_min", C.c_float), ("dt_max", C.c_float),
+        ("algo", C.c_int32)]
+
+
+class SsdBwd(C.Structure):
+    _fields_ = _T("x", "dt", "A", "B", "C", "D", "z", "dt_bias", "initial_states", "seq_idx", "dout", "dfinal_states",
+                  "dx", "ddt", "dB", "dC", "dz", "dinitial_states", "dA_part", "ddt_bias_part", "dD_part",
+                  "workspace") + [
+        ("chunk_size", C.c_int32), ("dt_softplus", C.c_int32), ("dt_min", C.c_float), ("dt_max", C.c_float),
+        ("algo", C.c_int32)]
+
+
+class NormGatedFwd(C.Structure):
+    _fields_ = _T("x", "weight", "bias", "z", "out", "rstd", "mean") + [
+        ("eps", C.c_float), ("group_size", C.c_int32), ("norm_before_gate", C.c_int32), ("is_rms_norm", C.c_int32)]
+
+
+class NormGatedBwd(C.Structure):
+    _fields_ = _T("x", "weight", "bias", "z", "dout", "rstd", "mean", "dx", "dz", "dw_part", "db_part",
+                  "out_recompute") + [
+        ("eps", C.c_float), ("group_size", C.c_int32), ("norm_before_gate", C.c_int32), ("is_rms_norm", C.c_int32)]
+
+
+class AddNormFwd(C.Structure):
+    _fields_ = _T("x", "residual", "weight", "bias", "y", "residual_out", "rstd", "mean") + [
+        ("eps", C.c_float), ("is_rms_norm", C.c_int32)]
+
+
+class AddNormBwd(C.Structure):
+    _fields_ = _T("xres", "weight", "bias", "dy", "dresidual_in", "rstd", "mean", "dx", "dresidual", "dw_part",
+                  "db_part") + [("eps", C.c_float), ("is_rms_norm", C.c_int32)]
+
+
+class Ssu(C.Structure):
+    _fields_ = _T("state", "x", "dt", "A", "B", "C", "D", "z", "dt_bias", "out") + [("dt_softplus", C.c_int32)]
+
+
+class SelScanFwd(C.Structure):
+    _fields_ = _T("u", "delta", "A", "B", "C", "D", "z", "delta_bias", "out", "last_state") + [
+        ("delta_softplus", C.c_int32)]
+
+
+class SelScanBwd(C.Structure):
+    _fields_ = _T("u", "delta", "A", "B", "C", "D", "z", "delta_bias", "dout", "du", "ddelta", "dB", "dC", "dz",
+                  "dA_part", "dD_part", "ddelta_bias_part", "workspace") + [("delta_softplus", C.c_int32)]
+
+
+# entry point -> params struct (every symbol include/omnissm.h declares with a params pointer)
+ENTRY_POINTS = {
+    "omni_causal_conv1d_fwd": Conv1dFwd,
+    "omni_causal_conv1d_bwd": Conv1dBwd,
+    "omni_causal_conv1d_update": Conv1dUpdate,
+    "omni_ssd_chunk_scan_fwd": SsdFwd,
+    "omni_ssd_chunk_scan_bwd": SsdBwd,
+    "omni_norm_gated_fwd": NormGatedFwd,
+    "omni_norm_gated_bwd": NormGatedBwd,
+    "omni_add_norm_fwd": AddNormFwd,
+    "omni_add_norm_bwd": AddNormBwd,
+    "omni_selective_state_update": Ssu,
+    "omni_selective_scan_fwd": SelScanFwd,
+    "omni_selective_scan_bwd": SelScanBwd,
+}
+OTHER_SYMBOLS = ["omni_version", "omni_last_error", "omni_launch_count", "omni_reset_launch_count",
+                 "omni_ssd_bwd_workspace_elems"]
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libomnissm.so")
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load libomnissm.so (once).  Raises if it has not been built - there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m omnimamba_b200.build` (needs nvcc). "
+            "omnimamba_b200 has no CPU or PyTorch fallback for its CUDA kernels.")
+    l = C.CDLL(LIB_PATH)
+    for name, struct in ENTRY_POINTS.items():
+        fn = getattr(l, name)
+        fn.argtypes = [C.POINTER(struct), C.c_void_p]
+        fn.restype = C.c_int
+    l.omni_version.restype = C.c_int
+    l.omni_last_error.restype = C.c_char_p
+    l.omni_launch_count.restype = C.c_int64
+    l.omni_reset_launch_count.restype = None
+    l.omni_ssd_bwd_workspace_elems.argtypes = [C.c_int64] * 5
+    l.omni_ssd_bwd_workspace_elems.restype = C.c_int64
+    _lib = l
+    return l
+
+
+def tdesc(t: Optional[torch.Tensor]) -> Tensor:
+    """Describe a CUDA tensor (or None -> absent) for the C ABI."""
+    d = Tensor()
+    if t is None:
+        return d
+    if not t.is_cuda:
+        raise RuntimeError("omnimamba_b200 kernels need CUDA tensors (no CPU fallback); got a tensor on " + str(t.device))
+    if t.dtype not in _DTYPES:
+        raise TypeError(f"unsupported dtype {t.dtype}")
+    if t.dim() > OMNI_MAX_DIMS:
+        raise ValueError("too many dimensions")
+    d.data = t.data_ptr() if t.numel() > 0 else 0
+    if t.numel() == 0:
+        # keep "present" semantics for empty tensors: give them a non-null dummy address
+        d.data = 1 << 4
+    d.dtype = _DTYPES[t.dtype]
+    d.ndim = t.dim()
+    for i in range(t.dim()):
+        d.shape[i] = t.shape[i]
+        d.stride[i] = t.stride(i)
+    return d
+
+
+def call(name: str, params: C.Structure, device: torch.device) -> None:
+    """Invoke an entry point on the current stream of `device`; raise on a non-zero status."""
+    l = lib()
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = getattr(l, name)(C.byref(params), C.c_void_p(stream))
+    if rc != 0:
+        msg = l.omni_last_error().decode("utf-8", "replace")
+        kind = _STATUS.get(rc, str(rc))
+        if rc in (1, 2, 3):
+            raise ValueError(f"{name}: {kind}: {msg}")
+        if rc == 4:
+            raise NotImplementedError(f"{name}: {msg}")
+        raise RuntimeError(f"{name}: {kind}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().omni_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().omni_reset_launch_count()
+
+
+def ssd_bwd_workspace_elems(batch, seqlen, nheads, headdim, dstate) -> int:
+    return int(lib().omni_ssd_bwd_workspace_elems(batch, seqlen, nheads, headdim, dstate))

@@ -1,0 +1,519 @@
+// Depthwise causal conv1d: forward, backward, decode update.  HBM-bound streaming kernels.
+//
+// Replaces causal_conv1d_fn / causal_conv1d_update of causal-conv1d==1.4.0
+// (/root/reference/requirements.txt:12) as reached from Mamba2.forward / Mamba2.step
+// (/root/reference/models/stage2/block.py:117).  Arithmetic: SURVEY.md Appendix A.2.
+//
+// Layout: the hot call passes xBC as a transposed slice of zxbcdt, i.e. (B, D, L) with
+// stride(D) == 1 ("channel-last", row pitch 8512 elements).  Each thread owns VEC consecutive
+// channels (one 16-byte vector) and walks TL consecutive tokens with the W-1 previous inputs kept
+// in registers, so every x / out element crosses HBM exactly once (+ (W-1)/TL halo re-reads that
+// hit L2).  A warp covers 32*VEC contiguous channels = 512 B per token row: fully coalesced.
+#include "common.cuh"
+
+namespace omni {
+namespace {
+
+constexpr int kMaxW = 4;
+constexpr int kTL = 64;       // tokens per thread
+constexpr int kSegs = 4;      // token segments (warps) per block
+
+struct ConvArgs {
+  const void* x; const void* w; const void* bias; const int* seq_idx; const void* init;
+  void* out; void* fin;
+  const void* dout; void* dx; float* dw; float* db; void* dinit;
+  int64_t xs_b, xs_d, xs_l, os_b, os_d, os_l;     // x / out (fwd) strides
+  int64_t gs_b, gs_d, gs_l, ds_b, ds_d, ds_l;     // dout / dx strides (bwd)
+  int64_t ws_d, ws_w, bs_d;
+  int64_t is_b, is_d, is_k, fs_b, fs_d, fs_k, dis_b, dis_d, dis_k;
+  int64_t ss_b, ss_l;
+  int B, D, L;
+  int w_dtype, b_dtype;
+  int silu;
+};
+
+template <typename T, int VEC> __device__ __forceinline__ void ldv(const T* p, float (&o)[VEC]) {
+  if constexpr (VEC == 1) o[0] = to_f<T>(*p);
+  else load_vec<T, VEC>(p, o);
+}
+template <typename T, int VEC> __device__ __forceinline__ void stv(T* p, const float (&o)[VEC]) {
+  if constexpr (VEC == 1) *p = from_f<T>(o[0]);
+  else store_vec<T, VEC>(p, o);
+}
+
+// x at token t (t may be negative => initial state / zero) for this thread's channels
+template <typename T, int VEC, int W>
+__device__ __forceinline__ void load_tok(const ConvArgs& a, int b, int d0, int t, float (&o)[VEC]) {
+  if (t >= 0) {
+    if (t < a.L) ldv<T, VEC>(static_cast<const T*>(a.x) + b * a.xs_b + d0 * a.xs_d + t * a.xs_l, o);
+    else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o[v] = 0.f;
+    }
+  } else if (a.init != nullptr) {
+    const T* ip = static_cast<const T*>(a.init) + b * a.is_b + (int64_t)(W - 1 + t) * a.is_k;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) o[v] = to_f<T>(ip[(d0 + v) * a.is_d]);
+  } else {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) o[v] = 0.f;
+  }
+}
+
+template <typename T, int VEC, int W>
+__global__ void __launch_bounds__(32 * kSegs) conv1d_fwd_kernel(ConvArgs a) {
+  const int d0 = (blockIdx.x * 32 + threadIdx.x) * VEC;
+  const int b = blockIdx.z;
+  const int t0 = (blockIdx.y * kSegs + threadIdx.y) * kTL;
+  if (d0 >= a.D) return;
+
+  // final states: the last W-1 inputs (done by the threads of the first segment)
+  if (a.fin != nullptr && t0 == 0) {
+    T* fp = static_cast<T*>(a.fin) + b * a.fs_b;
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k) {
+      float xv[VEC];
+      load_tok<T, VEC, W>(a, b, d0, a.L - (W - 1) + k, xv);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) fp[(d0 + v) * a.fs_d + k * a.fs_k] = from_f<T>(xv[v]);
+    }
+  }
+  if (t0 >= a.L) return;
+
+  float wgt[W][VEC], bia[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) wgt[k][v] = ld_any(a.w, a.w_dtype, (d0 + v) * a.ws_d + k * a.ws_w);
+    bia[v] = a.bias ? ld_any(a.bias, a.b_dtype, (d0 + v) * a.bs_d) : 0.f;
+  }
+  float win[W][VEC];  // win[k] = x[t - (W-1) + k]; win[W-1] is the current token
+  int sid[W];
+#pragma unroll
+  for (int k = 0; k < W - 1; ++k) {
+    load_tok<T, VEC, W>(a, b, d0, t0 - (W - 1) + k, win[k + 1]);
+    const int tt = t0 - (W - 1) + k;
+    sid[k + 1] = (a.seq_idx && tt >= 0) ? a.seq_idx[b * a.ss_b + tt * a.ss_l] : 0;
+  }
+  const int tend = min(t0 + kTL, a.L);
+  const T* xp = static_cast<const T*>(a.x) + b * a.xs_b + d0 * a.xs_d;
+  T* op = static_cast<T*>(a.out) + b * a.os_b + d0 * a.os_d;
+#pragma unroll 8
+  for (int t = t0; t < tend; ++t) {
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) win[k][v] = win[k + 1][v];
+      sid[k] = sid[k + 1];
+    }
+    ldv<T, VEC>(xp + t * a.xs_l, win[W - 1]);
+    sid[W - 1] = a.seq_idx ? a.seq_idx[b * a.ss_b + t * a.ss_l] : 0;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = bia[v];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      const bool same = (sid[k] == sid[W - 1]);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] += same ? wgt[k][v] * win[k][v] : 0.f;
+    }
+    if (a.silu) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = silu_f(acc[v]);
+    }
+    stv<T, VEC>(op + t * a.os_l, acc);
+  }
+}
+
+// Backward.  dc[t] = dout[t] * act'(c[t]);  dx[s] = sum_w weight[w] dc[s + W-1 - w];
+// dweight[w] = sum_t dc[t] x[t - (W-1) + w];  dbias = sum_t dc[t].
+template <typename T, int VEC, int W>
+__global__ void __launch_bounds__(32 * kSegs) conv1d_bwd_kernel(ConvArgs a) {
+  __shared__ float red[kSegs][32][VEC * (W + 1) + 1];
+  const int d0 = (blockIdx.x * 32 + threadIdx.x) * VEC;
+  const int b = blockIdx.z;
+  const int t0 = (blockIdx.y * kSegs + threadIdx.y) * kTL;
+  const bool active = d0 < a.D && t0 < a.L;
+
+  float dwa[W][VEC], dba[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    dba[v] = 0.f;
+#pragma unroll
+    for (int k = 0; k < W; ++k) dwa[k][v] = 0.f;
+  }
+  if (active) {
+    float wgt[W][VEC], bia[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+      for (int k = 0; k < W; ++k) wgt[k][v] = ld_any(a.w, a.w_dtype, (d0 + v) * a.ws_d + k * a.ws_w);
+      bia[v] = a.bias ? ld_any(a.bias, a.b_dtype, (d0 + v) * a.bs_d) : 0.f;
+    }
+    float win[W][VEC];   // x[t-(W-1) .. t]
+    float dcw[W][VEC];   // dcw[k] = dc[t - k]
+    float dia[W][VEC];   // dinitial_states accumulators (first segment only)
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) dia[k][v] = 0.f;
+    }
+    int sid[W];          // seq id of x window
+    int dsid[W];         // seq id of dc window (dsid[k] = seq[t-k])
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      dsid[k] = 0;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) dcw[k][v] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k) {
+      load_tok<T, VEC, W>(a, b, d0, t0 - (W - 1) + k, win[k + 1]);
+      const int tt = t0 - (W - 1) + k;
+      sid[k + 1] = (a.seq_idx && tt >= 0) ? a.seq_idx[b * a.ss_b + tt * a.ss_l] : 0;
+    }
+    const int own_end = min(t0 + kTL, a.L);
+    const int tlast = own_end + (W - 1);  // exclusive; dc beyond L is zero
+    const T* gp = static_cast<const T*>(a.dout) + b * a.gs_b + d0 * a.gs_d;
+    T* dxp = static_cast<T*>(a.dx) + b * a.ds_b + d0 * a.ds_d;
+    for (int t = t0; t < tlast; ++t) {
+#pragma unroll
+      for (int k = 0; k < W - 1; ++k) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) win[k][v] = win[k + 1][v];
+        sid[k] = sid[k + 1];
+      }
+#pragma unroll
+      for (int k = W - 1; k > 0; --k) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) dcw[k][v] = dcw[k - 1][v];
+        dsid[k] = dsid[k - 1];
+      }
+      float g[VEC];
+      if (t < a.L) {
+        load_tok<T, VEC, W>(a, b, d0, t, win[W - 1]);
+        sid[W - 1] = a.seq_idx ? a.seq_idx[b * a.ss_b + t * a.ss_l] : 0;
+        ldv<T, VEC>(gp + t * a.gs_l, g);
+        if (a.silu) {
+          float c[VEC];
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) c[v] = bia[v];
+#pragma unroll
+          for (int k = 0; k < W; ++k) {
+            const bool same = (sid[k] == sid[W - 1]);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) c[v] += same ? wgt[k][v] * win[k][v] : 0.f;
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) g[v] *= dsilu_f(c[v]);
+        }
+        if (t < own_end) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) dba[v] += g[v];
+#pragma unroll
+          for (int k = 0; k < W; ++k) {
+            const bool same = (sid[k] == sid[W - 1]);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) dwa[k][v] += same ? g[v] * win[k][v] : 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { g[v] = 0.f; win[W - 1][v] = 0.f; }
+        sid[W - 1] = -1;
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) dcw[0][v] = g[v];
+      dsid[0] = sid[W - 1];
+      // dinitial_states: "token" s = kk-(W-1) < 0 reached out[t] through tap kk - t
+      if (a.dinit != nullptr && t0 == 0 && t < W - 1) {
+#pragma unroll
+        for (int kk = 0; kk < W - 1; ++kk) {
+          const int wtap = kk - t;
+          if (wtap >= 0) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) dia[kk][v] += wgt[wtap][v] * g[v];
+          }
+        }
+      }
+      const int s = t - (W - 1);
+      if (s >= t0 && s < own_end) {
+        float r[VEC];
+        const int ssid = a.seq_idx ? a.seq_idx[b * a.ss_b + s * a.ss_l] : 0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = 0.f;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          // x[s] reached out[t-k] (t = s+W-1) through tap k
+          const bool same = !a.seq_idx || (dsid[k] == ssid);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) r[v] += same ? wgt[k][v] * dcw[k][v] : 0.f;
+        }
+        stv<T, VEC>(dxp + s * a.ds_l, r);
+      }
+    }
+    if (a.dinit != nullptr && t0 == 0) {
+      T* dip = static_cast<T*>(a.dinit) + b * a.dis_b;
+#pragma unroll
+      for (int kk = 0; kk < W - 1; ++kk) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) dip[(d0 + v) * a.dis_d + kk * a.dis_k] = from_f<T>(dia[kk][v]);
+      }
+    }
+  }
+  // reduce dweight / dbias over the block's token segments, then one atomic per (channel, tap)
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) red[threadIdx.y][threadIdx.x][v * (W + 1) + k] = dwa[k][v];
+    red[threadIdx.y][threadIdx.x][v * (W + 1) + W] = dba[v];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && d0 < a.D) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+      for (int k = 0; k <= W; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < kSegs; ++g) s += red[g][threadIdx.x][v * (W + 1) + k];
+        if (k < W) atomicAdd(a.dw + (int64_t)(d0 + v) * W + k, s);
+        else if (a.db) atomicAdd(a.db + d0 + v, s);
+      }
+    }
+  }
+}
+
+struct UpdArgs {
+  const void* x; void* st; const void* w; const void* bias; const int* cs; void* out;
+  int64_t xs_b, xs_d, xs_t, ss_b, ss_d, ss_s, os_b, os_d, os_t, ws_d, ws_w, bs_d;
+  int B, D, T, S, W;
+  int w_dtype, b_dtype, st_dtype;
+  int silu;
+};
+
+template <typename T>
+__global__ void conv1d_update_kernel(UpdArgs a) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (d >= a.D) return;
+  float wgt[kMaxW];
+#pragma unroll
+  for (int k = 0; k < kMaxW; ++k) wgt[k] = k < a.W ? ld_any(a.w, a.w_dtype, d * a.ws_d + k * a.ws_w) : 0.f;
+  const float bia = a.bias ? ld_any(a.bias, a.b_dtype, d * a.bs_d) : 0.f;
+  const T* xp = static_cast<const T*>(a.x) + b * a.xs_b + d * a.xs_d;
+  T* op = static_cast<T*>(a.out) + b * a.os_b + d * a.os_d;
+  char* sp = static_cast<char*>(a.st);
+  const int64_t sbase = b * a.ss_b + d * a.ss_d;
+  auto st_ld = [&](int i) { return ld_any(sp, a.st_dtype, sbase + i * a.ss_s); };
+  auto st_st = [&](int i, float v) { st_any(sp, a.st_dtype, sbase + i * a.ss_s, v); };
+  if (a.cs == nullptr) {
+    // window = [state(S) | x(T)], out[t] taps window[S + t - (W-1) + k]
+    for (int t = 0; t < a.T; ++t) {
+      float acc = bia;
+      for (int k = 0; k < a.W; ++k) {
+        const int i = a.S + t - (a.W - 1) + k;
+        const float v = i < a.S ? st_ld(i) : to_f<T>(xp[(i - a.S) * a.xs_t]);
+        acc += wgt[k] * v;
+      }
+      op[t * a.os_t] = from_f<T>(a.silu ? silu_f(acc) : acc);
+    }
+    for (int j = 0; j < a.S; ++j) {  // ascending: reads index T+j > j, not yet overwritten
+      const int i = a.T + j;
+      st_st(j, i < a.S ? st_ld(i) : to_f<T>(xp[(i - a.S) * a.xs_t]));
+    }
+  } else {
+    const int c0 = a.cs[b];
+    for (int t = 0; t < a.T; ++t) {
+      float acc = bia;
+      for (int k = 0; k < a.W; ++k) {
+        const int i = t - (a.W - 1) + k;  // relative to the new tokens
+        float v;
+        if (i >= 0) v = to_f<T>(xp[i * a.xs_t]);
+        else {
+          int pos = (c0 + i) % a.S;
+          if (pos < 0) pos += a.S;
+          v = st_ld(pos);
+        }
+        acc += wgt[k] * v;
+      }
+      op[t * a.os_t] = from_f<T>(a.silu ? silu_f(acc) : acc);
+    }
+    for (int t = 0; t < a.T; ++t) st_st((c0 + t) % a.S, to_f<T>(xp[t * a.xs_t]));
+  }
+}
+
+template <typename T, int VEC>
+int launch_fwd_w(const ConvArgs& a, int W, cudaStream_t s) {
+  dim3 block(32, kSegs), grid((a.D + 32 * VEC - 1) / (32 * VEC), (a.L + kSegs * kTL - 1) / (kSegs * kTL), a.B);
+  if (grid.y == 0) grid.y = 1;
+  switch (W) {
+    case 2: conv1d_fwd_kernel<T, VEC, 2><<<grid, block, 0, s>>>(a); break;
+    case 3: conv1d_fwd_kernel<T, VEC, 3><<<grid, block, 0, s>>>(a); break;
+    default: conv1d_fwd_kernel<T, VEC, 4><<<grid, block, 0, s>>>(a); break;
+  }
+  OMNI_CUDA_LAUNCH_CHECK("conv1d_fwd_kernel");
+  return OMNI_OK;
+}
+template <typename T, int VEC>
+int launch_bwd_w(const ConvArgs& a, int W, cudaStream_t s) {
+  dim3 block(32, kSegs), grid((a.D + 32 * VEC - 1) / (32 * VEC), (a.L + kSegs * kTL - 1) / (kSegs * kTL), a.B);
+  switch (W) {
+    case 2: conv1d_bwd_kernel<T, VEC, 2><<<grid, block, 0, s>>>(a); break;
+    case 3: conv1d_bwd_kernel<T, VEC, 3><<<grid, block, 0, s>>>(a); break;
+    default: conv1d_bwd_kernel<T, VEC, 4><<<grid, block, 0, s>>>(a); break;
+  }
+  OMNI_CUDA_LAUNCH_CHECK("conv1d_bwd_kernel");
+  return OMNI_OK;
+}
+
+// can this (B, D, L) view be accessed with VEC-wide vectors along D?
+bool vec_ok(const omni_tensor_t& t, int vec) {
+  return t.stride[1] == 1 && t.shape[1] % vec == 0 && t.stride[0] % vec == 0 && t.stride[2] % vec == 0 &&
+         aligned16(t.data);
+}
+
+int check_common(const omni_tensor_t& x, const omni_tensor_t& w, const omni_tensor_t& bias) {
+  OMNI_CHECK(x.ndim == 3, OMNI_BAD_SHAPE, "conv1d: x must be (batch, dim, seqlen)");
+  OMNI_CHECK(is_float_dtype(x.dtype), OMNI_BAD_DTYPE, "conv1d: x dtype");
+  OMNI_CHECK(w.ndim == 2 && w.shape[0] == x.shape[1], OMNI_BAD_SHAPE, "conv1d: weight must be (dim, width)");
+  OMNI_CHECK(w.shape[1] >= 2 && w.shape[1] <= kMaxW, OMNI_UNSUPPORTED, "conv1d: width must be 2..4");
+  OMNI_CHECK(is_float_dtype(w.dtype), OMNI_BAD_DTYPE, "conv1d: weight dtype");
+  if (present(bias)) {
+    OMNI_CHECK(bias.ndim == 1 && bias.shape[0] == x.shape[1], OMNI_BAD_SHAPE, "conv1d: bias must be (dim)");
+    OMNI_CHECK(is_float_dtype(bias.dtype), OMNI_BAD_DTYPE, "conv1d: bias dtype");
+  }
+  return OMNI_OK;
+}
+
+}  // namespace
+}  // namespace omni
+
+using namespace omni;
+
+extern "C" int omni_causal_conv1d_fwd(const omni_conv1d_fwd_params_t* p, void* stream) {
+  OMNI_CHECK(p != nullptr, OMNI_BAD_SHAPE, "null params");
+  if (int rc = check_common(p->x, p->weight, p->bias)) return rc;
+  const omni_tensor_t &x = p->x, &o = p->out;
+  OMNI_CHECK(present(o) && o.ndim == 3 && o.dtype == x.dtype, OMNI_BAD_SHAPE, "conv1d: out must match x");
+  for (int i = 0; i < 3; ++i) OMNI_CHECK(o.shape[i] == x.shape[i], OMNI_BAD_SHAPE, "conv1d: out shape != x shape");
+  const int W = (int)p->weight.shape[1];
+  ConvArgs a{};
+  a.x = x.data; a.w = p->weight.data; a.bias = p->bias.data; a.out = o.data;
+  a.B = (int)x.shape[0]; a.D = (int)x.shape[1]; a.L = (int)x.shape[2];
+  a.xs_b = x.stride[0]; a.xs_d = x.stride[1]; a.xs_l = x.stride[2];
+  a.os_b = o.stride[0]; a.os_d = o.stride[1]; a.os_l = o.stride[2];
+  a.ws_d = p->weight.stride[0]; a.ws_w = p->weight.stride[1]; a.bs_d = present(p->bias) ? p->bias.stride[0] : 0;
+  a.w_dtype = p->weight.dtype; a.b_dtype = p->bias.dtype; a.silu = p->activation == OMNI_ACT_SILU;
+  if (present(p->seq_idx)) {
+    OMNI_CHECK(p->seq_idx.dtype == OMNI_I32 && shape_is(p->seq_idx, 2, a.B, a.L), OMNI_BAD_SHAPE,
+               "conv1d: seq_idx must be int32 (batch, seqlen)");
+    a.seq_idx = static_cast<const int*>(p->seq_idx.data); a.ss_b = p->seq_idx.stride[0]; a.ss_l = p->seq_idx.stride[1];
+  }
+  if (present(p->initial_states)) {
+    OMNI_CHECK(shape_is(p->initial_states, 3, a.B, a.D, W - 1) && p->initial_states.dtype == x.dtype, OMNI_BAD_SHAPE,
+               "conv1d: initial_states must be (batch, dim, width-1) in x's dtype");
+    a.init = p->initial_states.data;
+    a.is_b = p->initial_states.stride[0]; a.is_d = p->initial_states.stride[1]; a.is_k = p->initial_states.stride[2];
+  }
+  if (present(p->final_states)) {
+    OMNI_CHECK(shape_is(p->final_states, 3, a.B, a.D, W - 1) && p->final_states.dtype == x.dtype, OMNI_BAD_SHAPE,
+               "conv1d: final_states must be (batch, dim, width-1) in x's dtype");
+    a.fin = p->final_states.data;
+    a.fs_b = p->final_states.stride[0]; a.fs_d = p->final_states.stride[1]; a.fs_k = p->final_states.stride[2];
+  }
+  if (a.B == 0 || a.D == 0) return OMNI_OK;
+  if (a.L == 0 && a.fin == nullptr) return OMNI_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return OMNI_DISPATCH_FLOAT(x.dtype, T, [&]() -> int {
+    constexpr int V = 16 / sizeof(T);
+    if (vec_ok(x, V) && vec_ok(o, V)) return launch_fwd_w<T, V>(a, W, s);
+    return launch_fwd_w<T, 1>(a, W, s);
+  });
+}
+
+extern "C" int omni_causal_conv1d_bwd(const omni_conv1d_bwd_params_t* p, void* stream) {
+  OMNI_CHECK(p != nullptr, OMNI_BAD_SHAPE, "null params");
+  if (int rc = check_common(p->x, p->weight, p->bias)) return rc;
+  const omni_tensor_t &x = p->x, &g = p->dout, &dx = p->dx;
+  OMNI_CHECK(present(g) && present(dx) && g.ndim == 3 && dx.ndim == 3 && g.dtype == x.dtype && dx.dtype == x.dtype,
+             OMNI_BAD_SHAPE, "conv1d bwd: dout/dx must match x");
+  for (int i = 0; i < 3; ++i)
+    OMNI_CHECK(g.shape[i] == x.shape[i] && dx.shape[i] == x.shape[i], OMNI_BAD_SHAPE, "conv1d bwd: shape mismatch");
+  const int W = (int)p->weight.shape[1];
+  OMNI_CHECK(present(p->dweight) && p->dweight.dtype == OMNI_F32 && shape_is(p->dweight, 2, x.shape[1], W) &&
+                 p->dweight.stride[1] == 1 && p->dweight.stride[0] == W,
+             OMNI_BAD_SHAPE, "conv1d bwd: dweight must be contiguous fp32 (dim, width)");
+  if (present(p->dbias))
+    OMNI_CHECK(p->dbias.dtype == OMNI_F32 && shape_is(p->dbias, 1, x.shape[1]) && p->dbias.stride[0] == 1,
+               OMNI_BAD_SHAPE, "conv1d bwd: dbias must be contiguous fp32 (dim)");
+  ConvArgs a{};
+  a.x = x.data; a.w = p->weight.data; a.bias = p->bias.data; a.dout = g.data; a.dx = dx.data;
+  a.dw = static_cast<float*>(p->dweight.data); a.db = static_cast<float*>(p->dbias.data);
+  a.B = (int)x.shape[0]; a.D = (int)x.shape[1]; a.L = (int)x.shape[2];
+  a.xs_b = x.stride[0]; a.xs_d = x.stride[1]; a.xs_l = x.stride[2];
+  a.gs_b = g.stride[0]; a.gs_d = g.stride[1]; a.gs_l = g.stride[2];
+  a.ds_b = dx.stride[0]; a.ds_d = dx.stride[1]; a.ds_l = dx.stride[2];
+  a.ws_d = p->weight.stride[0]; a.ws_w = p->weight.stride[1]; a.bs_d = present(p->bias) ? p->bias.stride[0] : 0;
+  a.w_dtype = p->weight.dtype; a.b_dtype = p->bias.dtype; a.silu = p->activation == OMNI_ACT_SILU;
+  if (present(p->seq_idx)) {
+    OMNI_CHECK(p->seq_idx.dtype == OMNI_I32 && shape_is(p->seq_idx, 2, a.B, a.L), OMNI_BAD_SHAPE,
+               "conv1d bwd: seq_idx must be int32 (batch, seqlen)");
+    a.seq_idx = static_cast<const int*>(p->seq_idx.data); a.ss_b = p->seq_idx.stride[0]; a.ss_l = p->seq_idx.stride[1];
+  }
+  if (present(p->initial_states)) {
+    OMNI_CHECK(shape_is(p->initial_states, 3, a.B, a.D, W - 1) && p->initial_states.dtype == x.dtype, OMNI_BAD_SHAPE,
+               "conv1d bwd: initial_states must be (batch, dim, width-1)");
+    a.init = p->initial_states.data;
+    a.is_b = p->initial_states.stride[0]; a.is_d = p->initial_states.stride[1]; a.is_k = p->initial_states.stride[2];
+  }
+  if (present(p->dinitial_states)) {
+    OMNI_CHECK(shape_is(p->dinitial_states, 3, a.B, a.D, W - 1) && p->dinitial_states.dtype == x.dtype, OMNI_BAD_SHAPE,
+               "conv1d bwd: dinitial_states must be (batch, dim, width-1)");
+    a.dinit = p->dinitial_states.data;
+    a.dis_b = p->dinitial_states.stride[0]; a.dis_d = p->dinitial_states.stride[1];
+    a.dis_k = p->dinitial_states.stride[2];
+  }
+  if (a.B == 0 || a.D == 0 || a.L == 0) return OMNI_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return OMNI_DISPATCH_FLOAT(x.dtype, T, [&]() -> int {
+    constexpr int V = 16 / sizeof(T);
+    if (vec_ok(x, V) && vec_ok(g, V) && vec_ok(dx, V)) return launch_bwd_w<T, V>(a, W, s);
+    return launch_bwd_w<T, 1>(a, W, s);
+  });
+}
+
+extern "C" int omni_causal_conv1d_update(const omni_conv1d_update_params_t* p, void* stream) {
+  OMNI_CHECK(p != nullptr, OMNI_BAD_SHAPE, "null params");
+  if (int rc = check_common(p->x, p->weight, p->bias)) return rc;
+  const omni_tensor_t &x = p->x, &st = p->conv_state, &o = p->out;
+  const int W = (int)p->weight.shape[1];
+  OMNI_CHECK(present(st) && st.ndim == 3 && st.shape[0] == x.shape[0] && st.shape[1] == x.shape[1] &&
+                 st.shape[2] >= W - 1 && is_float_dtype(st.dtype),
+             OMNI_BAD_SHAPE, "conv1d update: conv_state must be (batch, dim, state_len >= width-1)");
+  OMNI_CHECK(present(o) && o.ndim == 3 && o.dtype == x.dtype, OMNI_BAD_SHAPE, "conv1d update: out must match x");
+  for (int i = 0; i < 3; ++i) OMNI_CHECK(o.shape[i] == x.shape[i], OMNI_BAD_SHAPE, "conv1d update: out shape");
+  UpdArgs a{};
+  a.x = x.data; a.st = st.data; a.w = p->weight.data; a.bias = p->bias.data; a.out = o.data;
+  a.B = (int)x.shape[0]; a.D = (int)x.shape[1]; a.T = (int)x.shape[2]; a.S = (int)st.shape[2]; a.W = W;
+  a.xs_b = x.stride[0]; a.xs_d = x.stride[1]; a.xs_t = x.stride[2];
+  a.ss_b = st.stride[0]; a.ss_d = st.stride[1]; a.ss_s = st.stride[2];
+  a.os_b = o.stride[0]; a.os_d = o.stride[1]; a.os_t = o.stride[2];
+  a.ws_d = p->weight.stride[0]; a.ws_w = p->weight.stride[1]; a.bs_d = present(p->bias) ? p->bias.stride[0] : 0;
+  a.w_dtype = p->weight.dtype; a.b_dtype = p->bias.dtype; a.st_dtype = st.dtype;
+  a.silu = p->activation == OMNI_ACT_SILU;
+  if (present(p->cache_seqlens)) {
+    OMNI_CHECK(p->cache_seqlens.dtype == OMNI_I32 && shape_is(p->cache_seqlens, 1, a.B) &&
+                   p->cache_seqlens.stride[0] == 1,
+               OMNI_BAD_SHAPE, "conv1d update: cache_seqlens must be contiguous int32 (batch)");
+    a.cs = static_cast<const int*>(p->cache_seqlens.data);
+  }
+  if (a.B == 0 || a.D == 0 || a.T == 0) return OMNI_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 block(128), grid((a.D + 127) / 128, a.B);
+  return OMNI_DISPATCH_FLOAT(x.dtype, T, [&]() -> int {
+    conv1d_update_kernel<T><<<grid, block, 0, s>>>(a);
+    OMNI_CUDA_LAUNCH_CHECK("conv1d_update_kernel");
+    return OMNI_OK;
+  });
+}
