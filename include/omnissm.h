@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OMNI_ABI_VERSION 1
+#define OMNI_ABI_VERSION 2
 #if defined(__GNUC__)
 #define OMNI_API __attribute__((visibility("default")))
 #else
@@ -45,7 +45,7 @@ typedef enum {
   OMNI_CUDA_ERROR = 5
 } omni_status_t;
 
-typedef enum { OMNI_F32 = 0, OMNI_F16 = 1, OMNI_BF16 = 2, OMNI_I32 = 3, OMNI_I64 = 4 } omni_dtype_t;
+typedef enum { OMNI_F32 = 0, OMNI_F16 = 1, OMNI_BF16 = 2, OMNI_I32 = 3, OMNI_I64 = 4, OMNI_U8 = 5 } omni_dtype_t;
 
 typedef enum { OMNI_ACT_NONE = 0, OMNI_ACT_SILU = 1 } omni_activation_t;
 
@@ -112,11 +112,15 @@ OMNI_API int omni_causal_conv1d_update(const omni_conv1d_update_params_t* p, voi
 typedef struct omni_ssd_fwd_params {
   omni_tensor_t x, dt, A, B, C, D, z, dt_bias, initial_states, seq_idx;
   omni_tensor_t out, final_states;
+  omni_tensor_t workspace; /* 1-D, contiguous, >= omni_ssd_fwd_workspace_bytes() bytes, 16B aligned; needed by the
+                            * tensor-core algorithm (AUTO falls back to the recurrence without it) */
   int32_t chunk_size; /* accepted for API parity; the result does not depend on it */
   int32_t dt_softplus;
   float dt_min, dt_max; /* dt_limit */
   int32_t algo;         /* omni_ssd_algo_t */
 } omni_ssd_fwd_params_t;
+OMNI_API int64_t omni_ssd_fwd_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim,
+                                              int64_t ngroups, int64_t dstate);
 OMNI_API int omni_ssd_chunk_scan_fwd(const omni_ssd_fwd_params_t* p, void* stream);
 
 /* Backward.  dout like out.  Outputs: dx like x; ddt (B, L, H) in dt's dtype (gradient w.r.t. the RAW dt);
@@ -221,6 +225,21 @@ typedef struct omni_selscan_bwd_params {
   int32_t delta_softplus;
 } omni_selscan_bwd_params_t;
 OMNI_API int omni_selective_scan_bwd(const omni_selscan_bwd_params_t* p, void* stream);
+
+/* ---- self test ------------------------------------------------------------------------------ */
+/* Runs the four tcgen05 GEMM forms (smem/TMEM operands, K-/MN-major, fp16 x bf16) the chunked SSD kernel is built
+ * from on one CTA; tests/test_gpu_tc.py checks the results.  Cm, Bm: bf16 [128][128]; X: bf16 [128][64];
+ * P, Xs, S: fp32 [128][128]; D1 = Cm Bm^T, D3 = bf16(Xs) Bm, D4 = Cm bf16(S)^T: fp32 [128][128];
+ * D2 = f16(P) X: fp32 [128][64].  which: bit0 D1, bit1 D2, bit2 D4, bit3 D3, bit4 = P as bf16. */
+OMNI_API int omni_selftest(const void* Cm, const void* Bm, const void* X, const float* P, const float* Xs,
+                           const float* S, float* D1, float* D2, float* D3, float* D4, int which, void* stream);
+
+/* debug: CTA 0 of subsequent tensor-core SSD launches writes clock64() per (chunk, event) into buf[chunks*32]
+ * (device int64; NULL disables).  Used by scripts/trace_tc.py to find pipeline stalls. */
+OMNI_API void omni_debug_set_trace(void* buf, int chunks);
+/* debug: cycles for `iters` tcgen05.ld (mode 0/2: 4 KB each per warp) or 2x tcgen05.st (mode 1) per warp with nwarps warps
+ * issuing concurrently on one SM; out[warp] = cycles (device int64[128]). */
+OMNI_API int omni_debug_tmem_bench(long long* out, int mode, int nwarps, int iters, void* stream);
 
 #ifdef __cplusplus
 }

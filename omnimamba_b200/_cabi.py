@@ -13,13 +13,13 @@ from typing import Optional
 import torch
 
 OMNI_MAX_DIMS = 6
-OMNI_F32, OMNI_F16, OMNI_BF16, OMNI_I32, OMNI_I64 = 0, 1, 2, 3, 4
+OMNI_F32, OMNI_F16, OMNI_BF16, OMNI_I32, OMNI_I64, OMNI_U8 = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_SILU = 0, 1
 SSD_AUTO, SSD_RECURRENT, SSD_CHUNKED_TC = 0, 1, 2
 
 _DTYPES = {
     torch.float32: OMNI_F32, torch.float16: OMNI_F16, torch.bfloat16: OMNI_BF16,
-    torch.int32: OMNI_I32, torch.int64: OMNI_I64,
+    torch.int32: OMNI_I32, torch.int64: OMNI_I64, torch.uint8: OMNI_U8,
 }
 
 _STATUS = {1: "BAD_SHAPE", 2: "BAD_DTYPE", 3: "BAD_STRIDE", 4: "UNSUPPORTED", 5: "CUDA_ERROR"}
@@ -48,7 +48,8 @@ class Conv1dUpdate(C.Structure):
 
 
 class SsdFwd(C.Structure):
-    _fields_ = _T("x", "dt", "A", "B", "C", "D", "z", "dt_bias", "initial_states", "seq_idx", "out", "final_states") + [
+    _fields_ = _T("x", "dt", "A", "B", "C", "D", "z", "dt_bias", "initial_states", "seq_idx", "out", "final_states",
+                  "workspace") + [
         ("chunk_size", C.c_int32), ("dt_softplus", C.c_int32), ("dt_min", C.c_float), ("dt_max", C.c_float),
         ("algo", C.c_int32)]
 
@@ -112,7 +113,7 @@ ENTRY_POINTS = {
     "omni_selective_scan_bwd": SelScanBwd,
 }
 OTHER_SYMBOLS = ["omni_version", "omni_last_error", "omni_launch_count", "omni_reset_launch_count",
-                 "omni_ssd_bwd_workspace_elems"]
+                 "omni_ssd_bwd_workspace_elems", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench"]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libomnissm.so")
 _lib: Optional[C.CDLL] = None
@@ -138,6 +139,14 @@ def lib() -> C.CDLL:
     l.omni_reset_launch_count.restype = None
     l.omni_ssd_bwd_workspace_elems.argtypes = [C.c_int64] * 5
     l.omni_ssd_bwd_workspace_elems.restype = C.c_int64
+    l.omni_ssd_fwd_workspace_bytes.argtypes = [C.c_int64] * 6
+    l.omni_ssd_fwd_workspace_bytes.restype = C.c_int64
+    l.omni_selftest.argtypes = [C.c_void_p] * 10 + [C.c_int, C.c_void_p]
+    l.omni_selftest.restype = C.c_int
+    l.omni_debug_set_trace.argtypes = [C.c_void_p, C.c_int]
+    l.omni_debug_set_trace.restype = None
+    l.omni_debug_tmem_bench.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    l.omni_debug_tmem_bench.restype = C.c_int
     _lib = l
     return l
 
@@ -187,6 +196,10 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     lib().omni_reset_launch_count()
+
+
+def ssd_fwd_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate) -> int:
+    return int(lib().omni_ssd_fwd_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate))
 
 
 def ssd_bwd_workspace_elems(batch, seqlen, nheads, headdim, dstate) -> int:

@@ -32,7 +32,7 @@ void count_launch(int n = 1);
 
 inline bool present(const omni_tensor_t& t) { return t.data != nullptr; }
 inline bool is_float_dtype(int dt) { return dt == OMNI_F32 || dt == OMNI_F16 || dt == OMNI_BF16; }
-inline int dtype_size(int dt) { return dt == OMNI_F32 || dt == OMNI_I32 ? 4 : (dt == OMNI_I64 ? 8 : 2); }
+inline int dtype_size(int dt) { return dt == OMNI_F32 || dt == OMNI_I32 ? 4 : (dt == OMNI_I64 ? 8 : (dt == OMNI_U8 ? 1 : 2)); }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 inline bool shape_is(const omni_tensor_t& t, int nd, int64_t a = -1, int64_t b = -1, int64_t c = -1, int64_t d = -1,

@@ -171,7 +171,7 @@ def test_ssd_fwd_golden(ops):
     """The committed dense-formula golden vectors (tests/golden/ops_lib.npz)."""
     import os
     d = np.load(os.path.join(os.path.dirname(__file__), "golden", "ops_lib.npz"))
-    t = lambda k: torch.from_numpy(d[k]).to(DEV)
+    t = lambda k: torch.from_numpy(d[k]).float().to(DEV)
     out, fin = ops.mamba_chunk_scan_combined(t("ssd_x"), t("ssd_dt"), t("ssd_A"), t("ssd_B"), t("ssd_C"), 32, D=t("ssd_D"),
                                              dt_bias=t("ssd_dt_bias"), dt_softplus=True, return_final_states=True)
     check(out, torch.from_numpy(d["ssd_y"]), 1e-5, "golden ssd y")
