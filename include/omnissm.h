@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OMNI_ABI_VERSION 2
+#define OMNI_ABI_VERSION 3
 #if defined(__GNUC__)
 #define OMNI_API __attribute__((visibility("default")))
 #else
@@ -108,7 +108,8 @@ OMNI_API int omni_causal_conv1d_update(const omni_conv1d_update_params_t* p, voi
  * dt_softplus, dt_limit, return_final_states)  [mamba_ssm/ops/triton/ssd_combined.py; SURVEY.md 8(a) a4].
  *   x, z, out: (B, L, H, P); dt: (B, L, H); A: (H) fp32; B, C: (B, L, G, N);
  *   D: (H) or (H, P); dt_bias: (H); initial_states / final_states: (B, H, P, N) (final: fp32);
- *   seq_idx: (B, L) int32.  Innermost dims of x/z/out/B/C must be contiguous. */
+ *   seq_idx: (B, L) int32.  Innermost dims of x/z/out/B/C must be contiguous.  out may be fp32 while x is bf16
+ *   (the tensor-core kernel then stores its fp32 result unrounded; used by the parity tests). */
 typedef struct omni_ssd_fwd_params {
   omni_tensor_t x, dt, A, B, C, D, z, dt_bias, initial_states, seq_idx;
   omni_tensor_t out, final_states;
@@ -227,16 +228,19 @@ typedef struct omni_selscan_bwd_params {
 OMNI_API int omni_selective_scan_bwd(const omni_selscan_bwd_params_t* p, void* stream);
 
 /* ---- self test ------------------------------------------------------------------------------ */
-/* Runs the four tcgen05 GEMM forms (smem/TMEM operands, K-/MN-major, fp16 x bf16) the chunked SSD kernel is built
- * from on one CTA; tests/test_gpu_tc.py checks the results.  Cm, Bm: bf16 [128][128]; X: bf16 [128][64];
- * P, Xs, S: fp32 [128][128]; D1 = Cm Bm^T, D3 = bf16(Xs) Bm, D4 = Cm bf16(S)^T: fp32 [128][128];
- * D2 = f16(P) X: fp32 [128][64].  which: bit0 D1, bit1 D2, bit2 D4, bit3 D3, bit4 = P as bf16. */
+/* Runs the tcgen05 GEMM forms (smem/TMEM operands, K-/MN-major) the chunked SSD kernel is built from on one CTA;
+ * tests/test_gpu_tc.py checks the results.  Cm, Bm: 16-bit [128][128]; X: 16-bit [128][64] (bf16, or fp16 when bit8 of
+ * `which` is set); P, Xs, S: fp32 [128][128], rounded to the same 16-bit format inside;
+ * D1 = Cm Bm^T, D3 = r(Xs) Bm, D4 = Cm r(S)^T: fp32 [128][128]; D2 = r(P) X: fp32 [128][64].
+ * which: bit0 D1, bit1 D2, bit2 D4, bit3 D3 (A in TMEM), bit6 D3 (A = Xs^T as an MN-major smem operand), bit8 fp16. */
 OMNI_API int omni_selftest(const void* Cm, const void* Bm, const void* X, const float* P, const float* Xs,
                            const float* S, float* D1, float* D2, float* D3, float* D4, int which, void* stream);
 
 /* debug: CTA 0 of subsequent tensor-core SSD launches writes clock64() per (chunk, event) into buf[chunks*32]
  * (device int64; NULL disables).  Used by scripts/trace_tc.py to find pipeline stalls. */
 OMNI_API void omni_debug_set_trace(void* buf, int chunks);
+/* debug: suspend-time hint (ns) used by the mbarrier waits of the tensor-core SSD kernel (tuning experiments). */
+OMNI_API void omni_debug_set_mbar_hint(unsigned ns);
 /* debug: cycles for `iters` tcgen05.ld (mode 0/2: 4 KB each per warp) or 2x tcgen05.st (mode 1) per warp with nwarps warps
  * issuing concurrently on one SM; out[warp] = cycles (device int64[128]). */
 OMNI_API int omni_debug_tmem_bench(long long* out, int mode, int nwarps, int iters, void* stream);

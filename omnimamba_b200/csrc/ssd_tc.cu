@@ -2,31 +2,38 @@
 //
 // Replaces the five Triton kernels behind mamba_ssm's mamba_chunk_scan_combined (_chunk_cumsum, _chunk_state,
 // _state_passing, _bmm_chunk, _chunk_scan) with ONE persistent kernel that reads x, dt, B, C
-// once, writes y once and keeps the running (P x N) state on chip for the whole sequence.
+// once, writes y once and keeps the running (P x N) state on chip (fp32, in TMEM) for the whole sequence.
 //
 // Work item = (batch b, pair of heads h0, h0+1 of one group).  B_t / C_t are shared by the heads of a group, so two
 // heads are stacked along the MMA M dimension wherever the contraction allows it.  Per chunk of Q = 128 tokens:
 //   CB    [i][j]      = sum_n C[i][n] B[j][n]                    SS  M=128 N=128 K=128   (shared by both heads)
 //   Yoff  [i][(h,p)]  = sum_n C[i][n] S16[(h,p)][n]              SS  M=128 N=128 K=128   (state entering the chunk)
-//   S     [(h,p)][n] += sum_j X'[(h,p)][j] B[j][n]               TS  M=128 N=128 K=128   (fp32 state lives in TMEM)
-//   Ydiag_h[i][p]     = sum_j P_h[i][j] x_h[j][p]                TS  M=128 N=64  K=128   (per head)
+//   S     [(h,p)][n] += sum_j X'[j][(h,p)] B[j][n]               SS  M=128 N=128 K=128   (A MN-major; fp32 state lives in TMEM)
+//   Ydiag_h[i][p]     = sum_j P_h[i][j] x_h[j][p]                TS  M=128 N=64  K=128   (A = P in TMEM, per head)
 //   y_h[i][p] = Ydiag_h + exp(L_i) Yoff + D_h x_h[i][p]
 // with L = inclusive cumsum of dt*A inside the chunk, P_h[i][j] = CB[i][j] exp(L_i - L_j) dt_j (j <= i),
-// X'[(h,p)][j] = x_h[j][p] dt_j exp(L_last - L_j), and S <- exp(L_last) S before the accumulation.
+// X'[j][(h,p)] = x_h[j][p] dt_j exp(L_last - L_j) (the x tile scaled IN PLACE once Ydiag has consumed it), and
+// S <- exp(L_last) S before the accumulation.  Precision: every tensor-core operand is fp16, not bf16: the COMPUTED
+// operands (P, S16, X') carry 11 significant bits instead of 8, which keeps y within ~2e-4 of the fp32 reference before
+// the output rounding (bf16 operands give 2e-3).  A and B of one tcgen05.mma must share the 16-bit format (an fp16 x
+// bf16 kind::f16 MMA faults on sm_100a), so the bf16 inputs are converted too - exactly for 6.1e-5 <= |v| <= 65504
+// (saturating above, absolute error <= 3e-8 below): B and C (shared by all heads of a group) once per launch by a
+// streaming pre-pass into the caller's workspace, x in place in shared memory by the state-keeper warps.
 //
-// The only true scan is the scalar decay cumsum (one warp per head, shuffle scan: "table warps").  Precision: every
-// tensor-core operand is fp16, not bf16: the COMPUTED operands (P, S16, X') carry 11 significant bits instead of 8,
-// which is what keeps y within 1e-3 of the fp32 reference (bf16 operands give 2e-3, tests/test_gpu_tc.py).  bf16
-// inputs convert to fp16 exactly for 6.1e-5 <= |v| <= 65504 (saturating above, absolute error <= 3e-8 below): B and C
-// are converted once per launch by a streaming pre-pass into the caller's workspace, x is converted in place in
-// shared memory by the table warps.  All accumulators, dt, L and the state are fp32.
+// The only true scan is the scalar decay cumsum (one warp per head, Hillis-Steele shuffle scan: "table warps").
+// All accumulators, dt, L and the state are fp32.
 //
-// Warp roles (512 threads, 1 CTA per SM):
-//   warp 0      TMA producer: x (2 heads), B, C tiles, 128B swizzle            warp 1   tcgen05.mma issuer
-//   warps 2,3   per-head dt / cumsum / decay tables, x -> fp16                          warps 4-7   P builders   (lane = i)
-//   warps 8-11  state keepers: S16 copy, decay rescale, X' (lane = (h,p))      warps 12-15 epilogue     (lane = i)
-// TMEM columns: [0,128) CB then P in place | [128,256) Yoff (Ydiag_h1 re-uses [128,192)) | [256,384) S |
-//               [384,448) X'^T | [448,512) Ydiag_h0.
+// Warp roles (512 threads, 1 CTA per SM; TMEM lane quadrant = warp % 4):
+//   warp 0      TMA producer (x and C one stage, B two stages; 128B swizzle)          warp 1   tcgen05.mma issuer
+//   warps 2,3   per-head dt / cumsum / decay tables
+//   warps 4-11  P builders (two per quadrant, split by 32-column blocks), then the x pass (lane = row i of one head:
+//               x -> fp16 in place, X' = x dt decay -> second tile, D x -> the Ydiag accumulator in TMEM)
+//   warps 12-15 state keepers (S16 copy + decay rescale, lane = (h,p)) and epilogue (lane = row i; y staged per warp
+//               in swizzled shared memory and written with TMA stores)
+// Tensor-pipe order per chunk g:  CB(g) | Yoff(g) | S-update(g) | Ydiag(g): the three that only need TMA tiles and the
+// state run while the P builders work; C(g) is free after Yoff(g) and B(g) after the S-update, so their next loads land
+// before CB(g+1).
+// TMEM columns: [0,128) CB then P in place | [128,256) S | [256,384) Yoff | [384,512) Ydiag (64 per head).
 #include <algorithm>
 #include <mutex>
 
@@ -42,11 +49,13 @@ constexpr int NS = 128;    // d_state
 constexpr int kThreads = 512;
 
 // shared-memory map (bytes, relative to the 1024B-aligned base)
-constexpr uint32_t SM_X = 0;            // [stage 2][head 2][Q rows x 128 B]            64 KB
-constexpr uint32_t SM_B = 65536;        // [stage 2][n-half 2][Q rows x 128 B]          64 KB
-constexpr uint32_t SM_C = 131072;       // [n-half 2][Q rows x 128 B]                   32 KB
-constexpr uint32_t SM_S = 163840;       // [n-half 2][128 (h,p) rows x 128 B] bf16      32 KB
-constexpr uint32_t SM_TAB = 196608;     // [stage 2] Tab
+constexpr uint32_t SM_XA = 0;           // [head 2][Q rows x 128 B]  x bf16 (TMA) -> fp16 in place            32 KB
+constexpr uint32_t SM_XB = 32768;       // [head 2][Q rows x 128 B]  X' = x dt exp(lam_last - lam_j), fp16     32 KB
+constexpr uint32_t SM_B = 65536;        // [stage 2][n-half 2][Q rows x 128 B] fp16                            64 KB
+constexpr uint32_t SM_C = 131072;       // [n-half 2][Q rows x 128 B] fp16                                     32 KB
+constexpr uint32_t SM_S = 163840;       // [n-half 2][128 (h,p) rows x 128 B] fp16                             32 KB
+constexpr uint32_t SM_Y = 196608;       // [epilogue warp 4][32 rows x 128 B] y staging for the TMA stores     16 KB
+constexpr uint32_t SM_TAB = 212992;     // [stage 2] Tab
 struct Tab {
   float lam[2][Q];      // log2(e) * inclusive cumsum of dt*A  (all exps are ex2)
   float dtv[2][Q];      // transformed dt
@@ -61,21 +70,22 @@ struct Tab {
 static_assert(sizeof(Tab) % 16 == 0, "Tab alignment");
 constexpr uint32_t SM_BAR = SM_TAB + 2 * sizeof(Tab);
 enum {
-  B_FULL_X = 0, B_Y_WRITTEN = 2, B_FULL_B = 4, B_EMPTY_B = 6, B_TAB_READY = 8, B_TAB_FREE = 10, B_X16_READY = 12, B_XP_READY = 14,
-  B_FULL_C = 16, B_EMPTY_C, B_CB_DONE, B_P_READY, B_S_READY, B_R1_FREE, B_YOFF_DONE, B_YOFF0_READ, B_YD0_READ, B_U_DONE,
-  B_YD0_DONE, B_YD1_DONE, B_COUNT
+  B_FULL_B = 0, B_EMPTY_B = 2, B_TAB_READY = 4, B_TAB_FREE = 6,
+  B_FULL_C = 8, B_FULL_X, B_CB_DONE, B_P_READY, B_X16_READY, B_S_READY, B_YOFF_DONE, B_U_DONE, B_YD_DONE, B_ACC_FREE, B_COUNT
 };
 constexpr uint32_t SM_TMEMPTR = SM_BAR + B_COUNT * 8;
 constexpr uint32_t SM_TOTAL = SM_TMEMPTR + 16;
 constexpr uint32_t SMEM_BYTES = SM_TOTAL;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
-constexpr uint32_t TM_CB = 0, TM_YOFF = 128, TM_S = 256, TM_XP = 384;  // TM_XP: two 64-column buffers
+constexpr uint32_t TM_CB = 0, TM_S = 128, TM_YOFF = 256, TM_YD = 384;
 
 struct TcArgs {
   const void* dt; const float* A; const void* D; const void* dt_bias; const void* init; float* fin;
-  int64_t dt_b, dt_l, dt_h, i_b, i_h, i_p;
+  const __nv_bfloat16* x; void* out;
+  int64_t dt_b, dt_l, dt_h, i_b, i_h, i_p, x_b, x_l, x_h, o_b, o_l, o_h;
   int B, L, H, G;
-  int dt_dtype, D_dtype, dtb_dtype, init_dtype;
+  int dt_dtype, D_dtype, dtb_dtype, init_dtype, out_dtype;
   int dt_softplus;
   float dt_min, dt_max;
   long long* trace; int trace_chunks;  // debug: per-event clock64 of CTA 0 (omni_debug_set_trace)
@@ -93,9 +103,6 @@ __device__ __forceinline__ float ex2f(float v) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ float f16lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }
-__device__ __forceinline__ float f16hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
 __device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -121,14 +128,8 @@ __device__ __forceinline__ float2 u2f2(uint32_t lo, uint32_t hi) { return make_f
 __device__ __forceinline__ float2 h2f2(uint32_t v) {  // packed fp16 pair -> two fp32
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t saddr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr) : "memory");
-}
-// 16 lanes x 8 columns: r0 -> (lane T/4, col T%4), r1 -> (lane T/4 + 8, col T%4), r2/r3 -> the same lanes, col + 4
-__device__ __forceinline__ void tmem_st_16x128b_x2(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
-  asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-               : "memory");
+__device__ __forceinline__ float2 bf2f2(uint32_t v) {  // packed bf16 pair -> two fp32 (exact)
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
@@ -143,6 +144,14 @@ __device__ __forceinline__ float softplus_fast(float v) {
   return fmaxf(v, 0.f) + l;
 }
 
+// Walks the chunks of this CTA's work items in processing order (one integer division per item, not per chunk).
+struct ChunkIter {
+  int item, c, b, h0;
+};
+
+// Code size matters here: sixteen warps run five different role loops, and with everything unrolled the kernel was 130 KB
+// of SASS - far beyond the 32 KB instruction cache level - so a third of all issue slots were lost to instruction
+// fetch (ncu stall_no_inst).  Inner loops are therefore kept rolled (#pragma unroll 1) wherever the body is large.
 __global__ void __launch_bounds__(kThreads, 1)
 ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapY, TcArgs a) {
@@ -153,27 +162,21 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[B_FULL_X + i], 1);
-      mbar_init(&bars[B_Y_WRITTEN + i], 4);
       mbar_init(&bars[B_FULL_B + i], 1);
       mbar_init(&bars[B_EMPTY_B + i], 1);
       mbar_init(&bars[B_TAB_READY + i], 2);
       mbar_init(&bars[B_TAB_FREE + i], 12);
-      mbar_init(&bars[B_X16_READY + i], 2);
-      mbar_init(&bars[B_XP_READY + i], 4);
     }
     mbar_init(&bars[B_FULL_C], 1);
-    mbar_init(&bars[B_EMPTY_C], 1);
+    mbar_init(&bars[B_FULL_X], 1);
     mbar_init(&bars[B_CB_DONE], 1);
-    mbar_init(&bars[B_P_READY], 4);
+    mbar_init(&bars[B_P_READY], 8);
+    mbar_init(&bars[B_X16_READY], 8);
     mbar_init(&bars[B_S_READY], 4);
-    mbar_init(&bars[B_R1_FREE], 4);
     mbar_init(&bars[B_YOFF_DONE], 1);
-    mbar_init(&bars[B_YOFF0_READ], 4);
-    mbar_init(&bars[B_YD0_READ], 4);
     mbar_init(&bars[B_U_DONE], 1);
-    mbar_init(&bars[B_YD0_DONE], 1);
-    mbar_init(&bars[B_YD1_DONE], 1);
+    mbar_init(&bars[B_YD_DONE], 1);
+    mbar_init(&bars[B_ACC_FREE], 4);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -193,27 +196,132 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   const int hpg = a.H / a.G;                  // heads per group
   const uint32_t my_items = blockIdx.x < (uint32_t)nitems ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint32_t total = my_items * nchunks;  // chunks this CTA processes; g = running chunk counter (barrier phases)
-  // (batch, first head, chunk) of running chunk g
-  auto locate = [&](uint32_t g, int& b, int& h0, int& c) {
-    const int item = blockIdx.x + (g / nchunks) * gridDim.x;
-    c = g % nchunks;
-    b = item / HP;
-    h0 = (item % HP) * 2;
+  auto it_set = [&](ChunkIter& it, int item) {
+    it.item = item; it.c = 0; it.b = item / HP; it.h0 = (item - it.b * HP) * 2;
+  };
+  auto it_next = [&](ChunkIter& it) {
+    if (++it.c == nchunks) it_set(it, it.item + gridDim.x);
   };
 
-  if (warp < 2) {
-    // ============ table warps (one head each): dt transform, decay cumsum, exp tables; x tile -> fp16 in place =====
-    const int hh = warp;
+  if (warp == 0) {
+    // ============ TMA producer ========================================================================================
+    if (lane == 0 && total > 0) {
+      auto load_b = [&](const ChunkIter& it, uint32_t st) {
+        mbar_expect_tx(&bars[B_FULL_B + st], 32768);
+        tma_load_4d(smem + SM_B + st * 32768, &mapB, &bars[B_FULL_B + st], 0, it.h0 / hpg, it.c * Q, it.b);
+        tma_load_4d(smem + SM_B + st * 32768 + 16384, &mapB, &bars[B_FULL_B + st], 64, it.h0 / hpg, it.c * Q, it.b);
+      };
+      auto load_c = [&](const ChunkIter& it) {
+        mbar_expect_tx(&bars[B_FULL_C], 32768);
+        tma_load_4d(smem + SM_C, &mapC, &bars[B_FULL_C], 0, it.h0 / hpg, it.c * Q, it.b);
+        tma_load_4d(smem + SM_C + 16384, &mapC, &bars[B_FULL_C], 64, it.h0 / hpg, it.c * Q, it.b);
+      };
+      auto load_x = [&](const ChunkIter& it) {
+        mbar_expect_tx(&bars[B_FULL_X], 32768);
+        tma_load_4d(smem + SM_XA, &mapX, &bars[B_FULL_X], 0, it.h0, it.c * Q, it.b);
+        tma_load_4d(smem + SM_XA + 16384, &mapX, &bars[B_FULL_X], 0, it.h0 + 1, it.c * Q, it.b);
+      };
+      auto prefetch = [&](const ChunkIter& it) {  // pull a later chunk's x / C tiles into L2 (B is loaded two chunks ahead)
+        tma_prefetch_4d(&mapC, 0, it.h0 / hpg, it.c * Q, it.b);
+        tma_prefetch_4d(&mapC, 64, it.h0 / hpg, it.c * Q, it.b);
+        tma_prefetch_4d(&mapX, 0, it.h0, it.c * Q, it.b);
+        tma_prefetch_4d(&mapX, 0, it.h0 + 1, it.c * Q, it.b);
+      };
+      ChunkIter it1, it2;  // chunks g + 1 and g + 2
+      it_set(it1, blockIdx.x);
+      load_c(it1); load_b(it1, 0); load_x(it1);
+      it_next(it1);
+      it2 = it1;
+      if (total > 1) { load_b(it1, 1); prefetch(it1); }
+      it_next(it2);
+#pragma unroll 1
+      for (uint32_t g = 0; g + 1 < total; ++g) {
+        if (g + 2 < total) prefetch(it2);
+        mbar_wait(&bars[B_YOFF_DONE], g & 1);              // Yoff(g) has read C(g)
+        TR(2);
+        load_c(it1);
+        if (g + 2 < total) {
+          mbar_wait(&bars[B_EMPTY_B + (g & 1)], (g >> 1) & 1);  // S-update(g) has read B stage g & 1
+          TR(1);
+          load_b(it2, g & 1);
+        }
+        mbar_wait(&bars[B_YD_DONE], g & 1);                // Ydiag(g) has read x(g)
+        TR(0);
+        load_x(it1);
+        it_next(it1);
+        it_next(it2);
+      }
+    }
+  } else if (warp == 1) {
+    // ============ MMA issuer ==========================================================================================
+    if (lane == 0 && total > 0) {
+      const uint32_t id_nn = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
+      const uint32_t id_u = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorMN, kMajorMN);
+      const uint32_t id_yd = make_idesc(128, 64, kFmtF16, kFmtF16, kMajorK, kMajorMN);
+      // descriptors of k-step 0; k-major tiles advance by 32 B inside a 64-wide half and by 16 KB between halves,
+      // mn-major tiles by 16 rows = 2 KB (the address field counts 16-byte units)
+      const uint64_t dC = make_sdesc(smem_u32(smem + SM_C), 16, 1024), dS = make_sdesc(smem_u32(smem + SM_S), 16, 1024);
+      const uint64_t dXA = make_sdesc(smem_u32(smem + SM_XA), 16384, 1024), dXB = make_sdesc(smem_u32(smem + SM_XB), 16384, 1024);
+      const uint32_t has_D = a.D != nullptr ? 1u : 0u;
+#pragma unroll 1
+      for (uint32_t g = 0; g < total; ++g) {
+        const uint32_t st = g & 1, n = g >> 1, ph = g & 1;
+        const uint64_t dBk = make_sdesc(smem_u32(smem + SM_B + st * 32768), 16, 1024);
+        const uint64_t dBm = make_sdesc(smem_u32(smem + SM_B + st * 32768), 16384, 1024);
+        // CB = C B^T
+        mbar_wait(&bars[B_FULL_B + st], n & 1);
+        mbar_wait(&bars[B_FULL_C], ph);
+        tc_fence_after();
+        TR(3);
+#pragma unroll 1
+        for (uint32_t k = 0; k < 8; ++k) {
+          const uint32_t off = ((k >> 2) << 10) + ((k & 3) << 1);
+          mma_ss(tb + TM_CB, dC + off, dBk + off, id_nn, k > 0);
+        }
+        mma_commit(&bars[B_CB_DONE]);
+        // Yoff = C S16^T  (state entering the chunk)
+        mbar_wait(&bars[B_S_READY], ph);
+        if (g > 0) mbar_wait(&bars[B_ACC_FREE], ph ^ 1);
+        tc_fence_after();
+        TR(4);
+#pragma unroll 1
+        for (uint32_t k = 0; k < 8; ++k) {
+          const uint32_t off = ((k >> 2) << 10) + ((k & 3) << 1);
+          mma_ss(tb + TM_YOFF, dC + off, dS + off, id_nn, k > 0);
+        }
+        mma_commit(&bars[B_YOFF_DONE]);
+        // S += X'^T B   (S was rescaled by exp(lam_last) by the state keepers)
+        mbar_wait(&bars[B_X16_READY], ph);
+        tc_fence_after();
+        TR(5);
+#pragma unroll 1
+        for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + TM_S, dXB + k * 128, dBm + k * 128, id_u, true);
+        mma_commit(&bars[B_U_DONE]);
+        mma_commit(&bars[B_EMPTY_B + st]);
+        // Ydiag_h (+)= P_h x_h   (the accumulator already holds D x when D is given)
+        mbar_wait(&bars[B_P_READY], ph);
+        tc_fence_after();
+        TR(6);
+#pragma unroll 1
+        for (uint32_t hk = 0; hk < 16; ++hk) {
+          const uint32_t h = hk >> 3, k = hk & 7;
+          mma_ts(tb + TM_YD + 64 * h, tb + TM_CB + 32 * (k >> 1) + 16 * h + 8 * (k & 1), dXA + h * 1024 + k * 128, id_yd,
+                 (has_D | k) != 0);
+        }
+        mma_commit(&bars[B_YD_DONE]);
+      }
+    }
+  } else if (warp < 4) {
+    // ============ table warps (one head each): dt transform, decay cumsum, exp tables ================================
+    const int hh = warp - 2;
     uint32_t raw[4];  // raw dt bits of the NEXT chunk: loaded a chunk ahead, converted only when used
-    auto load_raw = [&](uint32_t g) {
-      int b, h0, c;
-      locate(g, b, h0, c);
-      const int64_t base = b * a.dt_b + (int64_t)(h0 + hh) * a.dt_h;
+    auto load_raw = [&](const ChunkIter& it, bool valid) {
+      const int64_t base = it.b * a.dt_b + (int64_t)(it.h0 + hh) * a.dt_h;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int t = c * Q + lane * 4 + k;
+        const int t = it.c * Q + lane * 4 + k;
         raw[k] = 0u;
-        if (g < total && t < a.L) {
+        if (valid && t < a.L) {
           if (a.dt_dtype == OMNI_F32) raw[k] = __ldg(static_cast<const uint32_t*>(a.dt) + base + (int64_t)t * a.dt_l);
           else raw[k] = __ldg(static_cast<const unsigned short*>(a.dt) + base + (int64_t)t * a.dt_l);
         }
@@ -224,11 +332,13 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       if (a.dt_dtype == OMNI_BF16) return __uint_as_float(bits << 16);
       return __half2float(__ushort_as_half((unsigned short)bits));
     };
-    load_raw(0);
+    ChunkIter it, itn;
+    it_set(it, blockIdx.x);
+    itn = it;
+    load_raw(it, total > 0);
+#pragma unroll 1
     for (uint32_t g = 0; g < total; ++g) {
-      int b, h0, c;
-      locate(g, b, h0, c);
-      const int h = h0 + hh;
+      const int h = it.h0 + hh, c = it.c;
       const uint32_t st = g & 1, n = g >> 1;
       Tab* tab = reinterpret_cast<Tab*>(smem + SM_TAB) + st;
       if (hh == 0) TR(8);
@@ -249,8 +359,8 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         run += v * Ah2;
         lam[k] = run;
       }
-      load_raw(g + 1);  // next chunk's raw dt: in flight while this chunk's tables are built
-      if (hh == 0) TR(28);
+      it_next(itn);
+      load_raw(itn, g + 1 < total);  // next chunk's raw dt: in flight while this chunk's tables are built
       float incl = run;  // warp inclusive scan of the per-lane totals (Hillis-Steele)
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -264,7 +374,6 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       float ref[3];
 #pragma unroll
       for (int w = 1; w < 4; ++w) ref[w - 1] = __shfl_sync(0xffffffffu, lam[3], 8 * w - 1);
-      if (hh == 0) TR(29);
       mbar_wait(&bars[B_TAB_FREE + st], (n & 1) ^ 1);
       if (hh == 0) TR(9);
       {
@@ -276,12 +385,13 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         reinterpret_cast<float4*>(tab->dtv[hh])[lane] = d4;
         reinterpret_cast<float4*>(tab->sj[hh])[lane] = s4;
         reinterpret_cast<float4*>(tab->eL[hh])[lane] = e4;
-#pragma unroll
+#pragma unroll 1
         for (int w = 1; w < 4; ++w)
           if (lane < 8 * w) {
+            const float rf = ref[w - 1];
             float4 v4;
-            v4.x = ex2f(ref[w - 1] - lam[0]) * dtv[0]; v4.y = ex2f(ref[w - 1] - lam[1]) * dtv[1];
-            v4.z = ex2f(ref[w - 1] - lam[2]) * dtv[2]; v4.w = ex2f(ref[w - 1] - lam[3]) * dtv[3];
+            v4.x = ex2f(rf - lam[0]) * dtv[0]; v4.y = ex2f(rf - lam[1]) * dtv[1];
+            v4.z = ex2f(rf - lam[2]) * dtv[2]; v4.w = ex2f(rf - lam[3]) * dtv[3];
             reinterpret_cast<float4*>(tab->v[hh][w - 1])[lane] = v4;
           }
         // diagonal blocks: reference = cumsum just before the lane's own 32-token block (0 for the first block)
@@ -299,413 +409,312 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       __syncwarp();
       if (hh == 0) TR(10);
       if (lane == 0) mbar_arrive(&bars[B_TAB_READY + st]);
-      // x_hh tile: bf16 -> fp16 in place (16-byte vectors; the swizzle only permutes whole 16-byte chunks)
-      mbar_wait(&bars[B_FULL_X + st], n & 1);
-      {
-        uint4* xt = reinterpret_cast<uint4*>(smem + SM_X + st * 32768 + hh * 16384);
-#pragma unroll 8
-        for (int q = 0; q < 32; ++q) {
-          uint4 v = xt[q * 32 + lane];
-          v.x = pack_f16_sat(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u));
-          v.y = pack_f16_sat(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
-          v.z = pack_f16_sat(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u));
-          v.w = pack_f16_sat(__uint_as_float(v.w << 16), __uint_as_float(v.w & 0xffff0000u));
-          xt[q * 32 + lane] = v;
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (hh == 0) TR(30);
-      if (lane == 0) mbar_arrive(&bars[B_X16_READY + st]);
+      it = itn;
     }
-  } else if (warp == 2) {
-    // ============ TMA: tile loads (x two stages, B two stages, C one) and y stores ==================================
-    if (lane == 0) {
-      for (uint32_t g = 0; g < total; ++g) {
-        int b, h0, c;
-        locate(g, b, h0, c);
-        const int grp = h0 / hpg, t0 = c * Q;
-        const uint32_t st = g & 1, n = g >> 1;
-        mbar_wait(&bars[B_EMPTY_B + st], (n & 1) ^ 1);
-        TR(1);
-        mbar_expect_tx(&bars[B_FULL_B + st], 32768);
-        tma_load_4d(smem + SM_B + st * 32768, &mapB, &bars[B_FULL_B + st], 0, grp, t0, b);
-        tma_load_4d(smem + SM_B + st * 32768 + 16384, &mapB, &bars[B_FULL_B + st], 64, grp, t0, b);
-        if (g >= 2) {  // y of chunk g-2 sits in x stage st: store it, then the stage can be refilled
-          int b2, h2, c2;
-          locate(g - 2, b2, h2, c2);
-          mbar_wait(&bars[B_Y_WRITTEN + st], (n & 1) ^ 1);
-          tma_store_4d(&mapY, smem + SM_X + st * 32768, 0, h2, c2 * Q, b2);
-          tma_store_4d(&mapY, smem + SM_X + st * 32768 + 16384, 0, h2 + 1, c2 * Q, b2);
-          tma_store_commit();
-          tma_store_wait_read<0>();
-        }
-        TR(0);
-        mbar_expect_tx(&bars[B_FULL_X + st], 32768);
-        tma_load_4d(smem + SM_X + st * 32768, &mapX, &bars[B_FULL_X + st], 0, h0, t0, b);
-        tma_load_4d(smem + SM_X + st * 32768 + 16384, &mapX, &bars[B_FULL_X + st], 0, h0 + 1, t0, b);
-        mbar_wait(&bars[B_EMPTY_C], (g & 1) ^ 1);
-        TR(2);
-        mbar_expect_tx(&bars[B_FULL_C], 32768);
-        tma_load_4d(smem + SM_C, &mapC, &bars[B_FULL_C], 0, grp, t0, b);
-        tma_load_4d(smem + SM_C + 16384, &mapC, &bars[B_FULL_C], 64, grp, t0, b);
-        if (g + 1 < total) {  // pull the next chunk's tiles into L2 so their TMA loads do not pay DRAM latency
-          int b1, h1, c1;
-          locate(g + 1, b1, h1, c1);
-          const int grp1 = h1 / hpg;
-          tma_prefetch_4d(&mapC, 0, grp1, c1 * Q, b1);
-          tma_prefetch_4d(&mapC, 64, grp1, c1 * Q, b1);
-          tma_prefetch_4d(&mapB, 0, grp1, c1 * Q, b1);
-          tma_prefetch_4d(&mapB, 64, grp1, c1 * Q, b1);
-          tma_prefetch_4d(&mapX, 0, h1, c1 * Q, b1);
-          tma_prefetch_4d(&mapX, 0, h1 + 1, c1 * Q, b1);
-        }
-      }
-      // drain: the last two chunks' y tiles
-      for (uint32_t g = total; g < total + 2; ++g) {
-        if (g < 2) continue;
-        int b2, h2, c2;
-        locate(g - 2, b2, h2, c2);
-        const uint32_t st = g & 1, n = g >> 1;
-        mbar_wait(&bars[B_Y_WRITTEN + st], (n & 1) ^ 1);
-        tma_store_4d(&mapY, smem + SM_X + st * 32768, 0, h2, c2 * Q, b2);
-        tma_store_4d(&mapY, smem + SM_X + st * 32768 + 16384, 0, h2 + 1, c2 * Q, b2);
-        tma_store_commit();
-      }
-      tma_store_wait_all<0>();
-    }
-  } else if (warp == 3) {
-    // ============ MMA issuer ==========================================================================================
-    if (lane == 0) {
-      const uint32_t id_nn = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
-      const uint32_t id_u = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorMN);
-      const uint32_t id_yd = make_idesc(128, 64, kFmtF16, kFmtF16, kMajorK, kMajorMN);
-      const uint32_t sC = smem_u32(smem + SM_C), sS = smem_u32(smem + SM_S);
-      for (uint32_t g = 0; g < total; ++g) {
-        const uint32_t st = g & 1, n = g >> 1, ph = g & 1;
-        const uint32_t sB = smem_u32(smem + SM_B + st * 32768), sX = smem_u32(smem + SM_X + st * 32768);
-        // CB = C B^T
-        mbar_wait(&bars[B_FULL_B + st], n & 1);
-        mbar_wait(&bars[B_FULL_C], ph);
-        tc_fence_after();
-        TR(3);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          mma_ss(tb + TM_CB, make_sdesc(sC + off, 16, 1024), make_sdesc(sB + off, 16, 1024), id_nn, k > 0);
-        }
-        mma_commit(&bars[B_CB_DONE]);
-        // Yoff = C S16^T  (state entering the chunk)
-        mbar_wait(&bars[B_S_READY], ph);
-        mbar_wait(&bars[B_R1_FREE], ph ^ 1);
-        tc_fence_after();
-        TR(4);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          mma_ss(tb + TM_YOFF, make_sdesc(sC + off, 16, 1024), make_sdesc(sS + off, 16, 1024), id_nn, k > 0);
-        }
-        mma_commit(&bars[B_YOFF_DONE]);
-        mma_commit(&bars[B_EMPTY_C]);
-        // S += X'^T B   (S was rescaled by exp(lam_last) by the state keepers)
-        mbar_wait(&bars[B_XP_READY + st], n & 1);
-        tc_fence_after();
-        TR(5);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          mma_ts(tb + TM_S, tb + TM_XP + st * 64 + k * 8, make_sdesc(sB + k * 2048, 16384, 1024), id_u, true);
-        mma_commit(&bars[B_U_DONE]);
-        mma_commit(&bars[B_EMPTY_B + st]);
-        // Ydiag_h0 = P_h0 x_h0 -> the drained Yoff_h0 columns
-        mbar_wait(&bars[B_P_READY], ph);
-        mbar_wait(&bars[B_X16_READY + st], n & 1);
-        mbar_wait(&bars[B_YOFF0_READ], ph);
-        tc_fence_after();
-        TR(6);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          mma_ts(tb + TM_YOFF, tb + TM_CB + 32 * (k >> 1) + 8 * (k & 1), make_sdesc(sX + k * 2048, 16384, 1024), id_yd, k > 0);
-        mma_commit(&bars[B_YD0_DONE]);
-        // Ydiag_h1 = P_h1 x_h1 -> the same columns once the epilogue has read Ydiag_h0
-        mbar_wait(&bars[B_YD0_READ], ph);
-        tc_fence_after();
-        TR(7);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          mma_ts(tb + TM_YOFF, tb + TM_CB + 32 * (k >> 1) + 16 + 8 * (k & 1), make_sdesc(sX + 16384 + k * 2048, 16384, 1024),
-                 id_yd, k > 0);
-        mma_commit(&bars[B_YD1_DONE]);
-      }
-    }
-  } else if (warp < 8) {
-    // ============ P builders (lane = row i): P_h = CB o decay o dt, fp16, written over CB in TMEM =====================
-    const int w = warp - 4, i = w * 32 + lane;
+  } else if (warp < 12) {
+    // ============ x pass + P builders ==================================================================================
+    // x pass: lane = row i of head `sub`; P build: lane = row i, 32-column blocks split between the two warps of a quadrant
+    const int pw = warp - 4, q = pw & 3, sub = pw >> 2, i = q * 32 + lane;
+    // blocks of this warp, 4 bits per step (block index | 4 = diagonal block | 8 = zero-fill): (quadrant, sub) ->
+    //   q3: {3d, 0} {1, 2}   q2: {2d} {0, 1, z3}   q1: {1d, z2} {0, z3}   q0: {0d} {z1, z2, z3}
+    const uint32_t plan = sub == 0 ? (q == 3 ? 0xF07u : q == 2 ? 0xFF6u : q == 1 ? 0xFA5u : 0xFF4u)
+                                   : (q == 3 ? 0xF21u : q == 2 ? 0xFB10u : q == 1 ? 0xFB0u : 0xFBA9u);
+    const uint32_t rx = (uint32_t)(i & 7) << 4;
+    const uint32_t xrow = sub * 16384 + i * 128;  // byte offset of this lane's x row inside the XA / XB tiles
+    ChunkIter it;
+    it_set(it, blockIdx.x);
+#pragma unroll 1
     for (uint32_t g = 0; g < total; ++g) {
       const uint32_t st = g & 1, n = g >> 1, ph = g & 1;
       const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
       mbar_wait(&bars[B_TAB_READY + st], n & 1);
-      if (w == 3) TR(11);
+      // ---- P build: P_h = CB o decay o dt (causal), fp16, written over CB in TMEM
       float lam_i[2], u_i[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         lam_i[h] = tab->lam[h][i];
-        u_i[h] = ex2f(lam_i[h] - (w > 0 ? tab->lam[h][32 * w - 1] : 0.f));
+        u_i[h] = ex2f(lam_i[h] - (q > 0 ? tab->lam[h][32 * q - 1] : 0.f));
       }
       const bool safe = tab->safe[0] != 0 && tab->safe[1] != 0;
       mbar_wait(&bars[B_CB_DONE], ph);
       tc_fence_after();
-      if (w == 3) TR(12);
+      if (pw == 3) TR(12);
 #pragma unroll 1
-      for (int jb = 0; jb < 4; ++jb) {
-        const uint32_t col = tmem_addr(tb, w * 32, TM_CB + 32 * jb);
-        if (jb > w) {
+      for (uint32_t pl = plan; (pl & 0xFu) != 0xFu; pl >>= 4) {
+        const int jb = pl & 3;
+        const uint32_t col = tmem_addr(tb, q * 32, TM_CB + 32 * jb);
+        if (pl & 8u) {  // above the diagonal
           uint32_t z[16];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) z[q] = 0u;
+          for (int e = 0; e < 16; ++e) z[e] = 0u;
           tmem_st16(col, z);
           tmem_st16(col + 16, z);
           continue;
         }
+        const bool diag = (pl & 4u) != 0;
         uint32_t cb[32];
         tmem_ld32(col, cb);
         tmem_ld_wait();
-#pragma unroll
+#pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           uint32_t pk[16];
-          if (jb < w || safe) {
-            const float4* vv = reinterpret_cast<const float4*>(jb < w ? &tab->v[h][w - 1][32 * jb] : &tab->vd[h][32 * jb]);
-            const float2 uu = make_float2(u_i[h], u_i[h]);
-            const int lim = jb < w ? 32 : lane;  // causal mask inside the diagonal block: column <= row
+          const float uh = h == 0 ? u_i[0] : u_i[1];
+          const float2 uu = make_float2(uh, uh);
+          if (!diag) {  // below the diagonal: no mask, row factor u_i x column table v
+            const float4* vv = reinterpret_cast<const float4*>(&tab->v[h][q - 1][32 * jb]);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 f = vv[q];
-              const float2 p01 = mul2(mul2(u2f2(cb[4 * q + 0], cb[4 * q + 1]), uu), make_float2(f.x, f.y));
-              const float2 p23 = mul2(mul2(u2f2(cb[4 * q + 2], cb[4 * q + 3]), uu), make_float2(f.z, f.w));
-              pk[2 * q] = pack_f16_sat(4 * q + 0 <= lim ? p01.x : 0.f, 4 * q + 1 <= lim ? p01.y : 0.f);
-              pk[2 * q + 1] = pack_f16_sat(4 * q + 2 <= lim ? p23.x : 0.f, 4 * q + 3 <= lim ? p23.y : 0.f);
+            for (int e = 0; e < 8; ++e) {
+              const float4 f = vv[e];
+              const float2 p01 = mul2(mul2(u2f2(cb[4 * e + 0], cb[4 * e + 1]), uu), make_float2(f.x, f.y));
+              const float2 p23 = mul2(mul2(u2f2(cb[4 * e + 2], cb[4 * e + 3]), uu), make_float2(f.z, f.w));
+              pk[2 * e] = pack_f16_sat(p01.x, p01.y);
+              pk[2 * e + 1] = pack_f16_sat(p23.x, p23.y);
             }
-          } else {  // diagonal block with extreme decay: direct exp2(lam_i - lam_j) dt_j, masked to j <= i
+          } else if (safe) {  // diagonal block: column <= row
+            const float4* vv = reinterpret_cast<const float4*>(&tab->vd[h][32 * jb]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 f = vv[e];
+              const float2 p01 = mul2(mul2(u2f2(cb[4 * e + 0], cb[4 * e + 1]), uu), make_float2(f.x, f.y));
+              const float2 p23 = mul2(mul2(u2f2(cb[4 * e + 2], cb[4 * e + 3]), uu), make_float2(f.z, f.w));
+              pk[2 * e] = pack_f16_sat(4 * e + 0 <= lane ? p01.x : 0.f, 4 * e + 1 <= lane ? p01.y : 0.f);
+              pk[2 * e + 1] = pack_f16_sat(4 * e + 2 <= lane ? p23.x : 0.f, 4 * e + 3 <= lane ? p23.y : 0.f);
+            }
+          } else {  // diagonal block with extreme decay: direct exp2(lam_i - lam_j) dt_j
             const float4* lj = reinterpret_cast<const float4*>(&tab->lam[h][32 * jb]);
             const float4* dj = reinterpret_cast<const float4*>(&tab->dtv[h][32 * jb]);
-            const float li = lam_i[h];
+            const float li = h == 0 ? lam_i[0] : lam_i[1];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 l4 = lj[q], d4 = dj[q];
-              const int j0 = 4 * q;  // column inside the block; row inside the block = lane
-              float2 e01 = make_float2(ex2f(li - l4.x), ex2f(li - l4.y));
-              float2 e23 = make_float2(ex2f(li - l4.z), ex2f(li - l4.w));
-              e01 = mul2(mul2(e01, make_float2(d4.x, d4.y)), u2f2(cb[4 * q + 0], cb[4 * q + 1]));
-              e23 = mul2(mul2(e23, make_float2(d4.z, d4.w)), u2f2(cb[4 * q + 2], cb[4 * q + 3]));
-              pk[2 * q] = pack_f16_sat(j0 + 0 <= lane ? e01.x : 0.f, j0 + 1 <= lane ? e01.y : 0.f);
-              pk[2 * q + 1] = pack_f16_sat(j0 + 2 <= lane ? e23.x : 0.f, j0 + 3 <= lane ? e23.y : 0.f);
+            for (int e = 0; e < 8; ++e) {
+              const float4 l4 = lj[e], d4 = dj[e];
+              float2 e01 = make_float2(ex2f(fminf(li - l4.x, 0.f)), ex2f(fminf(li - l4.y, 0.f)));
+              float2 e23 = make_float2(ex2f(fminf(li - l4.z, 0.f)), ex2f(fminf(li - l4.w, 0.f)));
+              e01 = mul2(mul2(e01, make_float2(d4.x, d4.y)), u2f2(cb[4 * e + 0], cb[4 * e + 1]));
+              e23 = mul2(mul2(e23, make_float2(d4.z, d4.w)), u2f2(cb[4 * e + 2], cb[4 * e + 3]));
+              pk[2 * e] = pack_f16_sat(4 * e + 0 <= lane ? e01.x : 0.f, 4 * e + 1 <= lane ? e01.y : 0.f);
+              pk[2 * e + 1] = pack_f16_sat(4 * e + 2 <= lane ? e23.x : 0.f, 4 * e + 3 <= lane ? e23.y : 0.f);
             }
           }
           tmem_st16(col + 16 * h, pk);
         }
-        if (w == 3) TR(24 + jb);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (w == 3) TR(13);
-      if (lane == 0) {
-        mbar_arrive(&bars[B_P_READY]);
-        mbar_arrive(&bars[B_TAB_FREE + st]);
+      if (pw == 3) TR(13);
+      if (lane == 0) mbar_arrive(&bars[B_P_READY]);
+      // ---- x pass: x row -> fp16 in place (Ydiag operand), X' row -> XB (state operand), D x -> Ydiag accumulator
+      const float sji = tab->sj[sub][i];
+      const float Dh = a.D ? ld_any(a.D, a.D_dtype, it.h0 + sub) : 0.f;
+      if (g > 0) {
+        mbar_wait(&bars[B_U_DONE], ph ^ 1);     // S-update(g-1) has read XB
+        mbar_wait(&bars[B_ACC_FREE], ph ^ 1);   // epilogue(g-1) has read the Ydiag accumulator
+        tc_fence_after();
       }
-    }
-  } else if (warp < 12) {
-    // ============ state keepers (TMEM lane r = (head, p)) ==============================================================
-    const int w = warp - 8, r = w * 32 + lane, hh = r >> 6, p = r & 63;
-    // X'^T(g) = (x dt exp(lam_last - lam_j))^T as the fp16 A operand of the state GEMM: ldmatrix.trans hands each thread
-    // (x[j][p], x[j+1][p]) pairs in exactly the (lane, column) pattern of a 16x128b TMEM store
-    auto build_xp = [&](uint32_t g) -> float {  // returns exp(lam_last) of chunk g (read before the tables are released)
-      const uint32_t st = g & 1, n = g >> 1;
-      const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
-      mbar_wait(&bars[B_TAB_READY + st], n & 1);
-      mbar_wait(&bars[B_X16_READY + st], n & 1);
-      if (w == 0) TR(17);
-      const uint32_t xs = smem_u32(smem + SM_X + st * 32768 + (w >> 1) * 16384);
-      const float* sj = tab->sj[w >> 1];
-      const float dch = tab->dchunk[w >> 1];
-      const int jrow = (lane & 7) + ((lane >> 4) << 3);      // row inside a 16-row step this lane addresses
-      const int csel = (lane >> 3) & 1;                      // which of the two 8-wide p chunks
+      mbar_wait(&bars[B_FULL_X], ph);
+      if (pw == 0) TR(17);
+      {
+        const float2 ss = make_float2(sji, sji), dd = make_float2(Dh, Dh);
+#pragma unroll 1
+        for (int k8 = 0; k8 < 8; k8 += 2) {  // two 16-byte chunks (16 columns) per step
+          uint32_t dx[16];
 #pragma unroll
-      for (int phalf = 0; phalf < 2; ++phalf) {
-        const int pc0 = 4 * (w & 1) + 2 * phalf;             // first 16-byte chunk (8 p) of this 16-lane half
-        const uint32_t tdst = tmem_addr(tb, w * 32 + 16 * phalf, TM_XP + st * 64);
-#pragma unroll
-        for (int js = 0; js < 8; ++js) {                     // 16 j per step
-          const int j0 = 16 * js;
-          uint32_t r0, r1, r2, r3;
-          ldsm_x4_trans(xs + sw128(j0 + jrow, pc0 + csel), r0, r1, r2, r3);
-          const float2 sa = *reinterpret_cast<const float2*>(sj + j0 + 2 * (lane & 3));
-          const float2 sb = *reinterpret_cast<const float2*>(sj + j0 + 8 + 2 * (lane & 3));
-          const float2 a0 = mul2(h2f2(r0), sa), a1 = mul2(h2f2(r1), sa), a2 = mul2(h2f2(r2), sb), a3 = mul2(h2f2(r3), sb);
-          tmem_st_16x128b_x2(tdst + 8 * js, pack_f16_sat(a0.x, a0.y), pack_f16_sat(a1.x, a1.y), pack_f16_sat(a2.x, a2.y),
-                             pack_f16_sat(a3.x, a3.y));
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t off = xrow + (((uint32_t)(k8 + k) << 4) ^ rx);
+            uint4 v = *reinterpret_cast<const uint4*>(smem + SM_XA + off);
+            const float2 f0 = bf2f2(v.x), f1 = bf2f2(v.y), f2 = bf2f2(v.z), f3 = bf2f2(v.w);
+            uint4 o16, op;
+            o16.x = pack_f16_sat(f0.x, f0.y); o16.y = pack_f16_sat(f1.x, f1.y);
+            o16.z = pack_f16_sat(f2.x, f2.y); o16.w = pack_f16_sat(f3.x, f3.y);
+            const float2 s0 = mul2(f0, ss), s1 = mul2(f1, ss), s2 = mul2(f2, ss), s3 = mul2(f3, ss);
+            op.x = pack_f16_sat(s0.x, s0.y); op.y = pack_f16_sat(s1.x, s1.y);
+            op.z = pack_f16_sat(s2.x, s2.y); op.w = pack_f16_sat(s3.x, s3.y);
+            *reinterpret_cast<uint4*>(smem + SM_XA + off) = o16;
+            *reinterpret_cast<uint4*>(smem + SM_XB + off) = op;
+            const float2 d0 = mul2(f0, dd), d1 = mul2(f1, dd), d2 = mul2(f2, dd), d3 = mul2(f3, dd);
+            dx[8 * k + 0] = __float_as_uint(d0.x); dx[8 * k + 1] = __float_as_uint(d0.y);
+            dx[8 * k + 2] = __float_as_uint(d1.x); dx[8 * k + 3] = __float_as_uint(d1.y);
+            dx[8 * k + 4] = __float_as_uint(d2.x); dx[8 * k + 5] = __float_as_uint(d2.y);
+            dx[8 * k + 6] = __float_as_uint(d3.x); dx[8 * k + 7] = __float_as_uint(d3.y);
+          }
+          if (a.D != nullptr) tmem_st16(tmem_addr(tb, q * 32, TM_YD + 64 * sub + 8 * k8), dx);
         }
       }
       tmem_st_wait();
+      fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (w == 0) TR(18);
+      if (pw == 0) TR(18);
       if (lane == 0) {
-        mbar_arrive(&bars[B_XP_READY + st]);
+        mbar_arrive(&bars[B_X16_READY]);
         mbar_arrive(&bars[B_TAB_FREE + st]);
       }
-      return dch;
-    };
-    auto write_final = [&](uint32_t glast) {  // state after running chunk glast (its U GEMM must be complete)
-      int b, h0, c;
-      locate(glast, b, h0, c);
-      float* dst = a.fin + ((int64_t)(b * a.H + h0 + hh) * HD + p) * NS;
+
+      it_next(it);
+    }
+  } else {
+    // ============ state keepers (TMEM lane r = (head, p)) + epilogue (lane = row i) ==================================
+    const int w = warp - 12, r = w * 32 + lane, hh = r >> 6, p = r & 63;
+    const uint32_t rx = (uint32_t)(r & 7) << 4;
+    uint8_t* ybuf = smem + SM_Y + w * 4096;
+    ChunkIter sn, ep;  // chunk gg (state step) and chunk gg - 1 (epilogue)
+    it_set(sn, blockIdx.x);
+    ep = sn;
+    // iteration gg = 0 .. total: [state step of chunk gg] then [epilogue of chunk gg - 1]
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
+    for (uint32_t gg = 0; gg < total + 1; ++gg) {
+      if (gg < total) {
+        // ---- S16 = fp16(S) for Yoff(gg);  S <- exp(lam_last(gg)) S  (initial state on the first chunk of an item)
+        const uint32_t g = gg;  // (for the trace macro)
+        const uint32_t st = gg & 1, n = gg >> 1;
+        const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
+        mbar_wait(&bars[B_TAB_READY + st], n & 1);
+        const float dch = tab->dchunk[hh];
+        if (gg > 0) {
+          mbar_wait(&bars[B_YOFF_DONE], (gg - 1) & 1);  // Yoff(gg-1) has read the S16 tile
+          mbar_wait(&bars[B_U_DONE], (gg - 1) & 1);     // S-update(gg-1) is complete
+          tc_fence_after();
+        }
+        if (w == 0) TR(15);
+        if (sn.c == 0) {
+          if (gg > 0 && a.fin) {  // final state of the item that just ended (the item of chunk gg - 1)
+            float* dst = a.fin + ((int64_t)(ep.b * a.H + ep.h0 + hh) * HD + p) * NS;
+#pragma unroll 1
+            for (int k4 = 0; k4 < 4; ++k4) {
+              uint32_t v[32];
+              tmem_ld32(tmem_addr(tb, w * 32, TM_S + 32 * k4), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; e += 4)
+                *reinterpret_cast<float4*>(dst + 32 * k4 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                            __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+            }
+          }
+          // state entering the item: initial_states or zero, through TMEM so that the hot loop below has one source
+          const int64_t ibase = sn.b * a.i_b + (int64_t)(sn.h0 + hh) * a.i_h + (int64_t)p * a.i_p;
+#pragma unroll 1
+          for (int k16 = 0; k16 < 8; ++k16) {
+            uint32_t v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = a.init ? __float_as_uint(ld_any(a.init, a.init_dtype, ibase + 16 * k16 + e)) : 0u;
+            tmem_st16(tmem_addr(tb, w * 32, TM_S + 16 * k16), v);
+          }
+          tmem_st_wait();
+        }
+        const float2 dd = make_float2(dch, dch);
+#pragma unroll 1
+        for (int k4 = 0; k4 < 4; ++k4) {
+          uint32_t v[32];
+          tmem_ld32(tmem_addr(tb, w * 32, TM_S + 32 * k4), v);
+          tmem_ld_wait();
+          uint8_t* srow = smem + SM_S + (k4 >> 1) * 16384 + r * 128;
+          const uint32_t c0 = (uint32_t)(k4 & 1) << 6;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16-byte chunks of 8 n
+            uint4 o;
+            o.x = pack_f16_sat(__uint_as_float(v[8 * k + 0]), __uint_as_float(v[8 * k + 1]));
+            o.y = pack_f16_sat(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3]));
+            o.z = pack_f16_sat(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5]));
+            o.w = pack_f16_sat(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7]));
+            *reinterpret_cast<uint4*>(srow + ((c0 + ((uint32_t)k << 4)) ^ rx)) = o;
+          }
+          uint32_t s0[16], s1[16];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float2 t0 = mul2(u2f2(v[e], v[e + 1]), dd), t1 = mul2(u2f2(v[16 + e], v[17 + e]), dd);
+            s0[e] = __float_as_uint(t0.x); s0[e + 1] = __float_as_uint(t0.y);
+            s1[e] = __float_as_uint(t1.x); s1[e + 1] = __float_as_uint(t1.y);
+          }
+          tmem_st16(tmem_addr(tb, w * 32, TM_S + 32 * k4), s0);
+          tmem_st16(tmem_addr(tb, w * 32, TM_S + 32 * k4 + 16), s1);
+        }
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (w == 0) TR(16);
+        if (lane == 0) mbar_arrive(&bars[B_S_READY]);
+        it_next(sn);
+      }
+      if (gg == 0) continue;
+      // ---- epilogue(g = gg - 1): y = Ydiag (+ D x) + exp(lam_i) Yoff, row i = r
+      const uint32_t g = gg - 1;
+      const uint32_t st = g & 1, ph = g & 1;
+      const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
+      const float eL0 = tab->eL[0][r], eL1 = tab->eL[1][r];
+      mbar_wait(&bars[B_YD_DONE], ph);   // Ydiag(g) is the last MMA of chunk g: Yoff(g) is complete as well
+      tc_fence_after();
+      if (w == 0) TR(19);
+      const int eb = ep.b, eh0 = ep.h0, ec = ep.c;
+      const int t = ec * Q + r;
+#pragma unroll 1
+      for (int s4 = 0; s4 < 4; ++s4) {  // s4 = head * 2 + 32-column half
+        const int hx = s4 >> 1, half = s4 & 1;
+        if (half == 0 && a.out_dtype == OMNI_BF16) {  // the staging tile is free once the previous TMA store has read it
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem_addr(tb, w * 32, TM_YOFF + 32 * s4), v0);
+        tmem_ld32(tmem_addr(tb, w * 32, TM_YD + 32 * s4), v1);
+        tmem_ld_wait();
+        const float eh = hx == 0 ? eL0 : eL1;
+        const float2 ee = make_float2(eh, eh);
+        float2 y[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) y[e] = fma2(u2f2(v0[2 * e], v0[2 * e + 1]), ee, u2f2(v1[2 * e], v1[2 * e + 1]));
+        if (a.out_dtype == OMNI_BF16) {
+          uint8_t* yrow = ybuf + lane * 128;
+          const uint32_t lx = (uint32_t)(lane & 7) << 4, c0 = (uint32_t)half << 6;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(yrow + ((c0 + ((uint32_t)k << 4)) ^ lx)) =
+                make_uint4(pack_bf16(y[4 * k].x, y[4 * k].y), pack_bf16(y[4 * k + 1].x, y[4 * k + 1].y),
+                           pack_bf16(y[4 * k + 2].x, y[4 * k + 2].y), pack_bf16(y[4 * k + 3].x, y[4 * k + 3].y));
+        } else if (t < a.L) {  // fp32 output (parity tests): straight to HBM
+          float4* dst = reinterpret_cast<float4*>(static_cast<float*>(a.out) + eb * a.o_b + (int64_t)t * a.o_l +
+                                                  (int64_t)(eh0 + hx) * a.o_h + 32 * half);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[k] = make_float4(y[2 * k].x, y[2 * k].y, y[2 * k + 1].x, y[2 * k + 1].y);
+        }
+        if (s4 == 3) {  // both accumulators have been read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&bars[B_ACC_FREE]);
+            mbar_arrive(&bars[B_TAB_FREE + st]);
+          }
+        }
+        if (half == 1 && a.out_dtype == OMNI_BF16) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && ec * Q + w * 32 < a.L) {  // rows beyond L are clipped by the tensor map
+            tma_store_4d(&mapY, ybuf, 0, eh0 + hx, ec * Q + w * 32, eb);
+            tma_store_commit();
+          }
+        }
+      }
+      if (w == 0) TR(22);
+      it_next(ep);
+    }
+    if (total > 0 && a.fin) {  // final state of the last item
+      mbar_wait(&bars[B_U_DONE], (total - 1) & 1);
+      tc_fence_after();
+      ChunkIter fl;
+      it_set(fl, blockIdx.x + (my_items - 1) * gridDim.x);
+      float* dst = a.fin + ((int64_t)(fl.b * a.H + fl.h0 + hh) * HD + p) * NS;
+#pragma unroll 1
+      for (int k4 = 0; k4 < 4; ++k4) {
         uint32_t v[32];
-        tmem_ld32(tmem_addr(tb, w * 32, TM_S + 32 * q), v);
+        tmem_ld32(tmem_addr(tb, w * 32, TM_S + 32 * k4), v);
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; e += 4)
-          *reinterpret_cast<float4*>(dst + 32 * q + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                                     __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          *reinterpret_cast<float4*>(dst + 32 * k4 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                      __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
       }
-    };
-    float dch = total > 0 ? build_xp(0) : 1.f;
-    for (uint32_t g = 0; g < total; ++g) {
-      int b, h0, c;
-      locate(g, b, h0, c);
-      const int h = h0 + hh;
-      const uint32_t ph = g & 1;
-      // S16 = fp16(S) for Yoff(g);  S <- exp(lam_last(g)) S  (or the initial state on the first chunk of an item)
-      if (g > 0) {
-        mbar_wait(&bars[B_U_DONE], ph ^ 1);
-        tc_fence_after();
-      }
-      if (w == 0) TR(15);
-      if (c == 0 && g > 0 && a.fin) write_final(g - 1);
-      const float2 dd = make_float2(dch, dch);
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        uint32_t v[32];
-        if (c == 0) {
-          if (a.init) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              v[e] = __float_as_uint(ld_any(a.init, a.init_dtype, b * a.i_b + h * a.i_h + p * a.i_p + 32 * q + e));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = 0u;
-          }
-        } else {
-          tmem_ld32(tmem_addr(tb, w * 32, TM_S + 32 * q), v);
-          tmem_ld_wait();
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 16-byte chunks of 8 n
-          uint4 o;
-          o.x = pack_f16_sat(__uint_as_float(v[8 * k + 0]), __uint_as_float(v[8 * k + 1]));
-          o.y = pack_f16_sat(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3]));
-          o.z = pack_f16_sat(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5]));
-          o.w = pack_f16_sat(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7]));
-          *reinterpret_cast<uint4*>(smem + SM_S + (q >> 1) * 16384 + sw128(r, (q & 1) * 4 + k)) = o;
-        }
-        uint32_t s0[16], s1[16];
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          const float2 t0 = mul2(u2f2(v[e], v[e + 1]), dd), t1 = mul2(u2f2(v[16 + e], v[17 + e]), dd);
-          s0[e] = __float_as_uint(t0.x); s0[e + 1] = __float_as_uint(t0.y);
-          s1[e] = __float_as_uint(t1.x); s1[e + 1] = __float_as_uint(t1.y);
-        }
-        tmem_st16(tmem_addr(tb, w * 32, TM_S + 32 * q), s0);
-        tmem_st16(tmem_addr(tb, w * 32, TM_S + 32 * q + 16), s1);
-      }
-      tmem_st_wait();
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (w == 0) TR(16);
-      if (lane == 0) mbar_arrive(&bars[B_S_READY]);
-      if (g + 1 < total) dch = build_xp(g + 1);
     }
-    if (total > 0 && a.fin) {
-      mbar_wait(&bars[B_U_DONE], (total - 1) & 1);
-      tc_fence_after();
-      write_final(total - 1);
-    }
-  } else {
-    // ============ epilogue (lane = row i): y = Ydiag + exp(lam_i) Yoff + D x -> bf16, over the x tile, TMA-stored ======
-    const int w = warp - 12, i = w * 32 + lane;
-    for (uint32_t g = 0; g < total; ++g) {
-      int b, h0, c;
-      locate(g, b, h0, c);
-      const uint32_t st = g & 1, n = g >> 1, ph = g & 1;
-      const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
-      float Dh[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) Dh[h] = a.D ? ld_any(a.D, a.D_dtype, h0 + h) : 0.f;
-      mbar_wait(&bars[B_TAB_READY + st], n & 1);
-      const float e0 = tab->eL[0][i], e1 = tab->eL[1][i];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_TAB_FREE + st]);
-      uint8_t* xb = smem + SM_X + st * 32768;
-      mbar_wait(&bars[B_YOFF_DONE], ph);
-      tc_fence_after();
-      if (w == 0) TR(19);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float2 acc[32];
-        const float2 ee = make_float2(h == 0 ? e0 : e1, h == 0 ? e0 : e1);
-        {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(tmem_addr(tb, w * 32, TM_YOFF + 64 * h), v0);
-          tmem_ld32(tmem_addr(tb, w * 32, TM_YOFF + 64 * h + 32), v1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            acc[e] = mul2(u2f2(v0[2 * e], v0[2 * e + 1]), ee);
-            acc[16 + e] = mul2(u2f2(v1[2 * e], v1[2 * e + 1]), ee);
-          }
-        }
-        if (h == 0) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[B_YOFF0_READ]);
-        }
-        mbar_wait(&bars[h == 0 ? B_YD0_DONE : B_YD1_DONE], ph);
-        tc_fence_after();
-        if (w == 0) TR(h == 0 ? 20 : 21);
-        {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(tmem_addr(tb, w * 32, TM_YOFF), v0);
-          tmem_ld32(tmem_addr(tb, w * 32, TM_YOFF + 32), v1);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[h == 0 ? B_YD0_READ : B_R1_FREE]);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            acc[e].x += __uint_as_float(v0[2 * e]); acc[e].y += __uint_as_float(v0[2 * e + 1]);
-            acc[16 + e].x += __uint_as_float(v1[2 * e]); acc[16 + e].y += __uint_as_float(v1[2 * e + 1]);
-          }
-        }
-        // + D x (x is fp16 in place), convert, overwrite the x tile with y (bf16)
-        const float2 dd = make_float2(Dh[h], Dh[h]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          uint4* ptr = reinterpret_cast<uint4*>(xb + h * 16384 + sw128(i, k));
-          const uint4 xv = *ptr;
-          const float2 y0 = fma2(h2f2(xv.x), dd, acc[4 * k + 0]), y1 = fma2(h2f2(xv.y), dd, acc[4 * k + 1]);
-          const float2 y2 = fma2(h2f2(xv.z), dd, acc[4 * k + 2]), y3 = fma2(h2f2(xv.w), dd, acc[4 * k + 3]);
-          uint4 o;
-          o.x = pack_bf16(y0.x, y0.y); o.y = pack_bf16(y1.x, y1.y); o.z = pack_bf16(y2.x, y2.y); o.w = pack_bf16(y3.x, y3.y);
-          *ptr = o;
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (w == 0) TR(22);
-      if (lane == 0) mbar_arrive(&bars[B_Y_WRITTEN + st]);
-    }
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -748,22 +757,28 @@ bool ssd_tc_fwd_supported(const omni_ssd_fwd_params_t* p) {
   if (!present(x) || x.ndim != 4 || x.dtype != OMNI_BF16 || x.shape[3] != HD || x.stride[3] != 1) return false;
   if (!present(Bm) || Bm.ndim != 4 || Bm.dtype != OMNI_BF16 || Bm.shape[3] != NS || Bm.stride[3] != 1) return false;
   if (!present(Cm) || Cm.ndim != 4 || Cm.dtype != OMNI_BF16 || Cm.shape[3] != NS || Cm.stride[3] != 1) return false;
-  if (!present(o) || o.ndim != 4 || o.dtype != OMNI_BF16 || o.stride[3] != 1) return false;
+  if (!present(o) || o.ndim != 4 || (o.dtype != OMNI_BF16 && o.dtype != OMNI_F32) || o.stride[3] != 1) return false;
   const int64_t H = x.shape[2], G = Bm.shape[2];
   if (G <= 0 || H % G != 0 || (H / G) % 2 != 0) return false;
   if (present(p->z) || present(p->seq_idx)) return false;
   if (present(p->D) && p->D.ndim != 1) return false;
   if (x.shape[1] < 1 || x.shape[0] < 1) return false;
-  for (const omni_tensor_t* t : {&x, &Bm, &Cm, &o}) {
-    if (!aligned16(t->data)) return false;
-    for (int d = 0; d < 3; ++d)
-      if (t->shape[d] > 1 && !tmap_stride_ok(t->stride[d])) return false;
-  }
-  if (present(p->final_states) && p->final_states.dtype != OMNI_F32) return false;
+  if (!aligned16(x.data)) return false;  // TMA: 16-byte aligned base and strides
+  for (int d = 0; d < 3; ++d)
+    if (x.shape[d] > 1 && !tmap_stride_ok(x.stride[d])) return false;
+  for (const omni_tensor_t* t : {&Bm, &Cm})  // the pre-pass reads B and C rows with 16-byte vectors
+    if (!aligned16(t->data) || (t->shape[2] > 1 && t->stride[2] % 8) || (t->shape[1] > 1 && t->stride[1] % 8) ||
+        (t->shape[0] > 1 && t->stride[0] % 8))
+      return false;
   const int64_t need = omni_ssd_fwd_workspace_bytes(x.shape[0], x.shape[1], H, HD, G, NS);
   const omni_tensor_t& ws = p->workspace;
   if (!present(ws) || ws.ndim != 1 || ws.stride[0] != 1 || ws.shape[0] * dtype_size(ws.dtype) < need || !aligned16(ws.data))
     return false;
+  // y rows are written with 16-byte vector stores
+  if (!aligned16(o.data)) return false;
+  for (int d = 0; d < 3; ++d)
+    if (o.shape[d] > 1 && (o.stride[d] * dtype_size(o.dtype)) % 16 != 0) return false;
+  if (present(p->final_states) && p->final_states.dtype != OMNI_F32) return false;
   return get_encode_tiled() != nullptr;
 }
 
@@ -778,6 +793,8 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
   TcArgs a{};
   a.dt = dt.data; a.dt_dtype = dt.dtype; a.dt_b = dt.stride[0]; a.dt_l = dt.stride[1]; a.dt_h = dt.stride[2];
   a.A = static_cast<const float*>(p->A.data);
+  a.x = static_cast<const __nv_bfloat16*>(x.data); a.x_b = x.stride[0]; a.x_l = x.stride[1]; a.x_h = x.stride[2];
+  a.out = o.data; a.out_dtype = o.dtype; a.o_b = o.stride[0]; a.o_l = o.stride[1]; a.o_h = o.stride[2];
   if (present(p->D)) {
     OMNI_CHECK(shape_is(p->D, 1, H) && is_float_dtype(p->D.dtype) && (H <= 1 || p->D.stride[0] == 1), OMNI_BAD_SHAPE,
                "ssd: D must be contiguous (H)");
@@ -821,20 +838,24 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
     ssd_tc_prep_kernel<<<dim3(gx, 2), 256, 0, s>>>(pa);
     OMNI_CUDA_LAUNCH_CHECK("ssd_tc_prep_kernel");
   }
-  auto tmap4 = [&](CUtensorMap* m, const void* base, const int64_t* shape, const int64_t* stride, bool bf16) -> int {
+  auto tmap4 = [&](CUtensorMap* m, const void* base, const int64_t* shape, const int64_t* stride, bool bf16, int rows) -> int {
     // dims innermost first: (inner, dim2, L, B); a size-1 dim may carry any stride: give TMA a harmless legal one
     const uint64_t dims[4] = {(uint64_t)shape[3], (uint64_t)shape[2], (uint64_t)shape[1], (uint64_t)shape[0]};
     auto st = [&](int d) { return (uint64_t)(shape[d] > 1 ? stride[d] : shape[3]) * 2; };
     const uint64_t strides[3] = {st(2), st(1), st(0)};
-    const uint32_t box[4] = {64, 1, (uint32_t)Q, 1};
+    const uint32_t box[4] = {64, 1, (uint32_t)rows, 1};
     return make_tmap_16bit(m, base, 4, dims, strides, box, bf16);
   };
   const int64_t bc_shape[4] = {Bsz, L, G, NS}, bc_stride[4] = {L * G * NS, G * NS, NS, 1};
   CUtensorMap mX, mB, mC, mY;
-  if (int rc = tmap4(&mX, x.data, x.shape, x.stride, true)) return rc;
-  if (int rc = tmap4(&mB, wsB, bc_shape, bc_stride, false)) return rc;
-  if (int rc = tmap4(&mC, wsC, bc_shape, bc_stride, false)) return rc;
-  if (int rc = tmap4(&mY, o.data, o.shape, o.stride, true)) return rc;
+  if (int rc = tmap4(&mX, x.data, x.shape, x.stride, true, Q)) return rc;
+  if (int rc = tmap4(&mB, wsB, bc_shape, bc_stride, false, Q)) return rc;
+  if (int rc = tmap4(&mC, wsC, bc_shape, bc_stride, false, Q)) return rc;
+  if (o.dtype == OMNI_BF16) {  // y leaves through per-warp TMA stores of 32 rows
+    if (int rc = tmap4(&mY, o.data, o.shape, o.stride, true, 32)) return rc;
+  } else {
+    mY = mX;  // unused by the fp32-output path
+  }
 
   static std::once_flag once[64];
   int dev = 0;
@@ -850,6 +871,9 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
 }
 
 }  // namespace omni
+
+// debug: suspend-time hint (ns) of the mbarrier waits inside the tensor-core SSD kernel
+extern "C" void omni_debug_set_mbar_hint(unsigned ns) { cudaMemcpyToSymbol(omni::umma::g_mbar_hint_ns, &ns, sizeof(ns)); }
 
 // debug: CTA 0 of the next ssd_tc launches records clock64() per (chunk, event) into buf[chunks * 32] (device int64)
 extern "C" void omni_debug_set_trace(void* buf, int chunks) {

@@ -24,14 +24,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread until the phase completes or the hint (ns) expires: without a hint the default limit is
+// a few cycles and sixteen warps spinning on barriers took a third of the SM's issue slots (ncu, profiles/).
+#ifndef OMNI_MBAR_HINT_NS
+#define OMNI_MBAR_HINT_NS 20000
+#endif
+static __device__ uint32_t g_mbar_hint_ns = OMNI_MBAR_HINT_NS;  // (tunable from the host for experiments: omni_debug_set_mbar_hint)
+#define kSuspendHintNs g_mbar_hint_ns
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }

@@ -4,6 +4,9 @@
 //   D2[i][p]      = sum_j f16(P[i][j]) X[j][p]       A: TMEM fp16 (tcgen05.st)    B: smem MN-major bf16 (TMA)  N=64
 //   D3[r][n]      = sum_j bf16(Xs[r][j]) B[j][n]     A: TMEM bf16 (tcgen05.st)    B: smem MN-major (TMA, LBO)  N=128
 //   D4[i][r]      = sum_n C[i][n] bf16(S[r][n])      A: smem K-major (TMA)        B: smem K-major (st.shared)  N=128
+//   bit6: D3 with A = Xs^T as an MN-major SMEM operand (SS form).  bit8: every operand fp16 instead of bf16.
+//   A and B of one tcgen05.mma must share the 16-bit format: kind::f16 with an fp16 A and a bf16 B raises an illegal-
+//   instruction fault on sm_100a (measured), which is why the SSD kernel converts B, C and x to fp16.
 #include "umma.cuh"
 
 namespace omni {
@@ -15,7 +18,7 @@ struct SelfArgs {
   const float* Xs;  // [128][128]
   const float* S;   // [128][128]
   float* D1; float* D2; float* D3; float* D4;
-  int which;  // bit0 D1, bit1 D2, bit2 D4, bit3 D3, bit4: P as bf16 instead of fp16
+  int which;  // bit0 D1, bit1 D2, bit2 D4, bit3 D3 (TS), bit6 D3 (SS, MN-major smem A), bit8 fp16 mode (else bf16)
 };
 
 __global__ void __launch_bounds__(128) selftest_kernel(const __grid_constant__ CUtensorMap mapC,
@@ -30,6 +33,8 @@ __global__ void __launch_bounds__(128) selftest_kernel(const __grid_constant__ C
   __shared__ uint64_t bar_tma, bar_mma;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool f16m = (a.which & 256) != 0;  // fp16 mode: Cm, Bm, X hold fp16 and every computed operand is packed as fp16
+  const int fmt = f16m ? kFmtF16 : kFmtBF16;
 
   if (tid == 0) {
     mbar_init(&bar_tma, 1);
@@ -57,8 +62,8 @@ __global__ void __launch_bounds__(128) selftest_kernel(const __grid_constant__ C
       uint32_t v[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c)
-        v[c] = (a.which & 16) ? pack_bf16(a.P[row * 128 + 2 * (c0 + c)], a.P[row * 128 + 2 * (c0 + c) + 1])
-                              : pack_f16(a.P[row * 128 + 2 * (c0 + c)], a.P[row * 128 + 2 * (c0 + c) + 1]);
+        v[c] = f16m ? pack_f16(a.P[row * 128 + 2 * (c0 + c)], a.P[row * 128 + 2 * (c0 + c) + 1])
+                    : pack_bf16(a.P[row * 128 + 2 * (c0 + c)], a.P[row * 128 + 2 * (c0 + c) + 1]);
       tmem_st16(tmem_addr(tb, warp * 32, 448 + c0), v);
     }
     tmem_st_wait();
@@ -67,7 +72,9 @@ __global__ void __launch_bounds__(128) selftest_kernel(const __grid_constant__ C
     for (int ch = 0; ch < 16; ++ch) {  // 16-byte chunks of 8 n
       uint32_t w[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = pack_bf16(a.S[row * 128 + ch * 8 + 2 * q], a.S[row * 128 + ch * 8 + 2 * q + 1]);
+      for (int q = 0; q < 4; ++q)
+        w[q] = f16m ? pack_f16(a.S[row * 128 + ch * 8 + 2 * q], a.S[row * 128 + ch * 8 + 2 * q + 1])
+                    : pack_bf16(a.S[row * 128 + ch * 8 + 2 * q], a.S[row * 128 + ch * 8 + 2 * q + 1]);
       uint8_t* dst = sS + (ch >> 3) * 16384 + sw128(row, ch & 7);
       *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -78,8 +85,8 @@ __global__ void __launch_bounds__(128) selftest_kernel(const __grid_constant__ C
   if (tid == 0) {
     tc_fence_after();
     mbar_wait(&bar_tma, 0);
-    const uint32_t idesc1 = make_idesc(128, 128, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
-    const uint32_t idesc2 = make_idesc(128, 64, (a.which & 16) ? kFmtBF16 : kFmtF16, kFmtBF16, kMajorK, kMajorMN);
+    const uint32_t idesc1 = make_idesc(128, 128, fmt, fmt, kMajorK, kMajorK);
+    const uint32_t idesc2 = make_idesc(128, 64, fmt, fmt, kMajorK, kMajorMN);
     const uint32_t idesc4 = idesc1;
     if (a.which & 1)
     for (int k = 0; k < 8; ++k) {  // D1 = C * B^T
@@ -119,14 +126,27 @@ __global__ void __launch_bounds__(128) selftest_kernel(const __grid_constant__ C
     tmem_st16(tmem_addr(tb, warp * 32, 448 + c0), v);
   }
   tmem_st_wait();
+  if (a.which & 64) {  // Xs^T as an fp16 MN-major smem A operand: element (j, r) in row j of the (r >> 6) half
+    for (int j = 0; j < 128; ++j) {
+      uint8_t* dst = sS + (row >> 6) * 16384 + sw128(j, (row & 63) >> 3) + (row & 7) * 2;
+      if (f16m) *reinterpret_cast<__half*>(dst) = __float2half_rn(a.Xs[row * 128 + j]);
+      else *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(a.Xs[row * 128 + j]);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
     tc_fence_after();
-    const uint32_t idesc3 = make_idesc(128, 128, kFmtBF16, kFmtBF16, kMajorK, kMajorMN);
+    const uint32_t idesc3 = make_idesc(128, 128, fmt, fmt, kMajorK, kMajorMN);
+    const uint32_t idesc5 = make_idesc(128, 128, fmt, fmt, kMajorMN, kMajorMN);
     if (a.which & 8)
     for (int k = 0; k < 8; ++k)
       mma_ts(tb + 192, tb + 448 + k * 8, make_sdesc(smem_u32(sB) + k * 2048, 16384, 1024), idesc3, k > 0);
+    if (a.which & 64)
+    for (int k = 0; k < 8; ++k)
+      mma_ss(tb + 192, make_sdesc(smem_u32(sS) + k * 2048, 16384, 1024), make_sdesc(smem_u32(sB) + k * 2048, 16384, 1024),
+             idesc5, k > 0);
     mma_commit(&bar_mma);
   }
   __syncthreads();

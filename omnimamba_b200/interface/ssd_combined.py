@@ -34,11 +34,9 @@ def ssd_fwd_raw(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initia
     p.D, p.z, p.dt_bias = abi.tdesc(D), abi.tdesc(z), abi.tdesc(dt_bias)
     p.initial_states, p.seq_idx = abi.tdesc(initial_states), abi.tdesc(seq_idx)
     p.out, p.final_states = abi.tdesc(out), abi.tdesc(fin)
-    ws = None
-    if algo != "recurrent" and x.dtype == torch.bfloat16:
-        # scratch for the tensor-core path (fp16 copies of B and C); the caching allocator makes this free in steady state
-        ws = torch.empty(abi.ssd_fwd_workspace_bytes(batch, seqlen, nheads, headdim, B.shape[-2], dstate), device=x.device,
-                         dtype=torch.uint8)
+    nws = abi.ssd_fwd_workspace_bytes(batch, seqlen, nheads, headdim, B.shape[-2], dstate) if algo != "recurrent" else 0
+    # scratch for the tensor-core path (fp16 copies of B and C); the caching allocator makes this free in steady state
+    ws = torch.empty(nws, device=x.device, dtype=torch.uint8) if nws > 0 and x.dtype == torch.bfloat16 else None
     p.workspace = abi.tdesc(ws)
     p.chunk_size, p.dt_softplus = int(chunk_size), int(bool(dt_softplus))
     p.dt_min, p.dt_max = float(dt_limit[0]), float(min(dt_limit[1], 3.0e38))

@@ -11,9 +11,9 @@ sys.path.insert(0, ROOT)
 from omnimamba_b200 import _cabi  # noqa: E402
 from omnimamba_b200.interface.ssd_combined import ssd_fwd_raw  # noqa: E402
 
-NAMES = {0: "tma:x_issue", 1: "tma:B_issue", 2: "tma:C_issue", 3: "mma:CB", 4: "mma:Yoff", 5: "mma:U", 6: "mma:Yd0", 7: "mma:Yd1",
-         8: "tab:start", 9: "tab:free", 10: "tab:ready", 11: "P:tab", 12: "P:cb_done", 13: "P:done", 14: "S:tab", 15: "S:u_done",
-         16: "S:s_ready", 17: "S:full_x", 18: "S:xp_ready", 19: "E:yoff", 20: "E:yd0", 21: "E:yd1", 22: "E:written", 23: "E:stored", 24: "P:blk0", 25: "P:blk1", 26: "P:blk2", 27: "P:blk3", 28: "tab:dtmath", 29: "tab:scanned", 30: "tab:x16"}
+NAMES = {0: "tma:x_issue(g+1)", 1: "tma:B_issue(g+2)", 2: "tma:C_issue(g+1)", 3: "mma:CB", 4: "mma:Yoff", 5: "mma:U", 6: "mma:Yd",
+         8: "tab:start", 9: "tab:free", 10: "tab:ready", 12: "P:cb_done", 13: "P:done", 15: "S:u_done(g-1)",
+         16: "S:s_ready", 17: "X:full_x", 18: "X:x16_ready", 19: "E:yd_done", 22: "E:stored"}
 
 
 def main():
