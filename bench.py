@@ -46,6 +46,15 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "ssd_fwd_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("dram_bytes_per_launch"), d.get("source")
+    return None, None
+
+
 def make_inputs(batch, seqlen, seed=0):
     """SURVEY.md 8(d) synthetic inputs on the HOST: x, B, C, raw dt ~ N(0,1) bf16; Mamba2-init dt_bias; A = -U(1,16); D = 1."""
     g = torch.Generator().manual_seed(seed)
@@ -115,30 +124,28 @@ def time_cuda(fn, steps, warmup, dist_on):
 
 
 def max_over_ranks(v, dist_on, device):
-    if not dist_on:
-        return v
-    t = torch.tensor([v], device=device, dtype=torch.float64)
-    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    return float(t.item())
+    from omnimamba_b200.dist import max_over_ranks as _max
+    return _max(v, device=device) if dist_on else v
 
 
-def cpu_arm(seconds_target=15.0, seqlen=None):
-    """The oracle's fp32 recurrent loop at d_model=2048, B=1, all host threads.  Returns (tokens/s, cores, sample)."""
+def cpu_arm(seconds_target=12.0, seqlen=4096):
+    """The oracle's fp32 recurrent loop at d_model=2048 (B=1, L=4096 sequences, all host threads), repeated until
+    `seconds_target` of CPU work is done.  Returns (tokens/s, threads, sample, tokens, seconds)."""
     import oracle
     torch.set_num_threads(os.cpu_count() or 1)
     from cases import scan_inputs
-    probe = 64
-    x, dt, A, Bm, Cm, D, dt_bias = scan_inputs(1, probe, H, P, G, N, 0, torch.float32)
-    t0 = time.perf_counter()
-    oracle.cpu_recurrent_baseline(x, dt, A, Bm, Cm, D, dt_bias)
-    per_tok = (time.perf_counter() - t0) / probe
-    if seqlen is None:
-        seqlen = int(max(128, min(4096, seconds_target / max(per_tok, 1e-9))))
     x, dt, A, Bm, Cm, D, dt_bias = scan_inputs(1, seqlen, H, P, G, N, 0, torch.float32)
-    t0 = time.perf_counter()
-    oracle.cpu_recurrent_baseline(x, dt, A, Bm, Cm, D, dt_bias)
-    el = time.perf_counter() - t0
-    return seqlen / el, torch.get_num_threads(), f"B=1 L={seqlen} d_model=2048 fp32 recurrent token loop ({el:.1f} s)", seqlen, el
+    oracle.cpu_recurrent_baseline(x[:, :64], dt[:, :64], A, Bm[:, :64], Cm[:, :64], D, dt_bias)  # warm the thread pool
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        oracle.cpu_recurrent_baseline(x, dt, A, Bm, Cm, D, dt_bias)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= seconds_target or reps >= 64:
+            break
+    toks = reps * seqlen
+    return (toks / el, torch.get_num_threads(),
+            f"{reps} x (B=1, L={seqlen}) d_model=2048 fp32 recurrent token loop, {el:.1f} s of CPU work", toks, el)
 
 
 def run_reference(args, rank):
@@ -146,20 +153,19 @@ def run_reference(args, rank):
     here) on the host cores; rank 0 only."""
     if rank != 0:
         return
-    seqlen = None
     times, toks = [], 0
-    per_step = min(8.0, max(0.5, 120.0 / (args.warmup + args.steps)))  # whole run ends within a few minutes
+    per_step = min(10.0, max(1.0, 150.0 / (args.warmup + args.steps)))  # whole run ends within a few minutes
     for i in range(args.warmup + args.steps):
-        tps, cores, sample, seqlen, el = cpu_arm(seconds_target=per_step, seqlen=seqlen)
+        tps, cores, sample, ntok, el = cpu_arm(seconds_target=per_step)
         if i >= args.warmup:
             times.append(el)
-            toks += seqlen
+            toks += ntok
     total = sum(times)
     v = toks / total
     line = {"metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"mamba_chunk_scan_combined fwd, d_model=2048 (H=64,P=64,G=1,N=128), bounded sample B=1 L={seqlen}",
+            "config": {"workload": "mamba_chunk_scan_combined fwd, d_model=2048 (H=64,P=64,G=1,N=128), bounded sample per step: " + sample,
                        "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,6 +203,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=device)
 
     from omnimamba_b200 import _cabi
+    from omnimamba_b200.dist import allreduce_param_grads
     from omnimamba_b200.interface.ssd_combined import mamba_chunk_scan_combined, ssd_bwd_raw, ssd_fwd_raw
     _cabi.lib()
 
@@ -220,7 +227,10 @@ def main():
     t_fwd = max_over_ranks(t_fwd, dist_on, device)
     value = world * tokens * args.steps / t_fwd
     hbm, how = peaks()
-    kernel_s = t_fwd / args.steps  # one kernel launch per step: the step IS the dominant kernel's duration
+    traffic, traffic_src = measured_traffic() if L == 4096 else (None, None)
+    # one C-ABI call per step = the streaming B/C fp16 pre-pass (~3 % of the time) + the persistent scan kernel; the whole
+    # call is charged to the roofline (conservative)
+    kernel_s = t_fwd / args.steps
     achieved = tokens * BYTES_FWD / kernel_s / 1e9
 
     # ---- fwd + bwd -----------------------------------------------------------------------------------------
@@ -232,9 +242,8 @@ def main():
             fwd()
             r = ssd_bwd_raw(dy, dev["x"], dev["dt"], dev["A"], dev["B"], dev["C"], 256, D=dev["D"], dt_bias=dev["dt_bias"],
                             dt_softplus=True, algo=args.algo)
-            if dist_on:  # DDP semantics: only parameter gradients cross NVLink
-                flat = torch.cat([r[2], r[5], r[7]])
-                torch.distributed.all_reduce(flat)
+            if dist_on:  # DDP semantics: only parameter gradients (dA, dD, ddt_bias) cross NVLink
+                allreduce_param_grads([r[2], r[5], r[7]])
 
         steps_fb = max(3, args.steps // 4)
         t_fb = max_over_ranks(time_cuda(fwd_bwd, steps_fb, 3, dist_on), dist_on, device)
@@ -278,8 +287,8 @@ def main():
                        "algo": args.algo, "parallelism": f"replicas x{world} (batch-sharded, no data-path collective)",
                        "l2": f"inputs+output {tokens * BYTES_FWD / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "peak_source": f"{how} (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback",
-                         "bytes_per_token": BYTES_FWD, "kernel": "ssd forward (one launch per step)"},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{how} (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback",
+                         "bytes_per_token": BYTES_FWD, "kernel": "ssd_tc_prep_kernel + ssd_tc_fwd_kernel (one C-ABI call per step)"},
             "fwd_bwd": fb, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
             "clocks": clk.summary(),
         }

@@ -163,8 +163,20 @@ def test_ssd_fwd(ops, dtype, shape, variant, algo):
     out, fin = ssd_fwd_raw(c(x), c(dt), c(A), c(Bm), c(Cm), 256, D=c(kw.get("D")), z=c(z), dt_bias=c(kw.get("dt_bias")),
                            initial_states=c(init), dt_softplus=kw["dt_softplus"],
                            dt_limit=kw.get("dt_limit", (0.0, float("inf"))), return_final_states=True, algo=algo)
-    check(out, ref, TOL[dtype], f"ssd out {variant}")
-    check(fin, fin_ref, TOL[dtype], f"ssd final_states {variant}")
+    if dtype == torch.bfloat16 and algo == "auto":
+        # may run on the tcgen05 kernel (fp16 tensor-core operands): excess-over-output-rounding metric against the
+        # UNROUNDED fp32 oracle, tests/parity_metric.py; its final states carry the fp16 rounding of X' (<= 3e-3 fp32)
+        from parity_metric import excess_over_rounding
+        f = lambda t: None if t is None else t.float()
+        ref32 = oracle.mamba_chunk_scan_combined_ref(f(x), dt, A, f(Bm), f(Cm), 256, z=f(z), initial_states=init, **kw)
+        assert ref32.dtype == torch.float32
+        e = excess_over_rounding(out, ref32)
+        assert e <= TOL[dtype], f"ssd out {variant}: excess over bf16 rounding {e:.3e}"
+        check(out, ref, 2e-3, f"ssd out {variant} (vs the bf16-rounded oracle: amplified metric, reported bound)")
+        check(fin, fin_ref, 3e-3, f"ssd final_states {variant}")
+    else:
+        check(out, ref, TOL[dtype], f"ssd out {variant}")
+        check(fin, fin_ref, TOL[dtype], f"ssd final_states {variant}")
 
 
 def test_ssd_fwd_golden(ops):
