@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OMNI_ABI_VERSION 3
+#define OMNI_ABI_VERSION 4
 #if defined(__GNUC__)
 #define OMNI_API __attribute__((visibility("default")))
 #else
@@ -128,9 +128,12 @@ OMNI_API int omni_ssd_chunk_scan_fwd(const omni_ssd_fwd_params_t* p, void* strea
  * dB, dC: (B, L, G, N) FP32, ZEROED by the caller; dz like z (optional); dinitial_states (B,H,P,N) fp32
  * optional; per-(batch, head) FP32 partials the caller sums over batch: dA_part, ddt_bias_part: (B, H),
  * dD_part: (B, H) or (B, H, P).  dfinal_states (B,H,P,N) optional incoming gradient.
- * workspace: FP32, omni_ssd_bwd_workspace_elems() elements. */
+ * workspace: 1-D, 256-byte aligned; omni_ssd_bwd_workspace_elems() FP32 elements for the recurrence,
+ * omni_ssd_bwd_tc_workspace_bytes() bytes for the tensor-core algorithm (AUTO uses the latter when
+ * the shapes/dtypes qualify and the workspace is large enough; dB/dC/dA_part/... contracts are the same). */
 typedef struct omni_ssd_bwd_params {
   omni_tensor_t x, dt, A, B, C, D, z, dt_bias, initial_states, seq_idx;
+  omni_tensor_t out; /* reserved (the forward's output, as upstream saves it); no algorithm reads it: pass an absent tensor */
   omni_tensor_t dout, dfinal_states;
   omni_tensor_t dx, ddt, dB, dC, dz, dinitial_states, dA_part, ddt_bias_part, dD_part;
   omni_tensor_t workspace;
@@ -141,6 +144,8 @@ typedef struct omni_ssd_bwd_params {
 } omni_ssd_bwd_params_t;
 OMNI_API int64_t omni_ssd_bwd_workspace_elems(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim,
                                      int64_t dstate);
+OMNI_API int64_t omni_ssd_bwd_tc_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim,
+                                                 int64_t ngroups, int64_t dstate);
 OMNI_API int omni_ssd_chunk_scan_bwd(const omni_ssd_bwd_params_t* p, void* stream);
 
 /* ---- gated RMSNorm / LayerNorm ------------------------------------------------------------ */
@@ -232,7 +237,8 @@ OMNI_API int omni_selective_scan_bwd(const omni_selscan_bwd_params_t* p, void* s
  * tests/test_gpu_tc.py checks the results.  Cm, Bm: 16-bit [128][128]; X: 16-bit [128][64] (bf16, or fp16 when bit8 of
  * `which` is set); P, Xs, S: fp32 [128][128], rounded to the same 16-bit format inside;
  * D1 = Cm Bm^T, D3 = r(Xs) Bm, D4 = Cm r(S)^T: fp32 [128][128]; D2 = r(P) X: fp32 [128][64].
- * which: bit0 D1, bit1 D2, bit2 D4, bit3 D3 (A in TMEM), bit6 D3 (A = Xs^T as an MN-major smem operand), bit8 fp16. */
+ * which: bit0 D1, bit1 D2, bit2 D4, bit3 D3 (A in TMEM), bit6 D3 (A = Xs^T as an MN-major smem operand),
+ * bit7 D3 (A = Xs as a K-major smem operand, B MN-major), bit8 fp16. */
 OMNI_API int omni_selftest(const void* Cm, const void* Bm, const void* X, const float* P, const float* Xs,
                            const float* S, float* D1, float* D2, float* D3, float* D4, int which, void* stream);
 

@@ -55,7 +55,7 @@ class SsdFwd(C.Structure):
 
 
 class SsdBwd(C.Structure):
-    _fields_ = _T("x", "dt", "A", "B", "C", "D", "z", "dt_bias", "initial_states", "seq_idx", "dout", "dfinal_states",
+    _fields_ = _T("x", "dt", "A", "B", "C", "D", "z", "dt_bias", "initial_states", "seq_idx", "out", "dout", "dfinal_states",
                   "dx", "ddt", "dB", "dC", "dz", "dinitial_states", "dA_part", "ddt_bias_part", "dD_part",
                   "workspace") + [
         ("chunk_size", C.c_int32), ("dt_softplus", C.c_int32), ("dt_min", C.c_float), ("dt_max", C.c_float),
@@ -113,7 +113,7 @@ ENTRY_POINTS = {
     "omni_selective_scan_bwd": SelScanBwd,
 }
 OTHER_SYMBOLS = ["omni_version", "omni_last_error", "omni_launch_count", "omni_reset_launch_count",
-                 "omni_ssd_bwd_workspace_elems", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint"]
+                 "omni_ssd_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint"]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libomnissm.so")
 _lib: Optional[C.CDLL] = None
@@ -139,6 +139,8 @@ def lib() -> C.CDLL:
     l.omni_reset_launch_count.restype = None
     l.omni_ssd_bwd_workspace_elems.argtypes = [C.c_int64] * 5
     l.omni_ssd_bwd_workspace_elems.restype = C.c_int64
+    l.omni_ssd_bwd_tc_workspace_bytes.argtypes = [C.c_int64] * 6
+    l.omni_ssd_bwd_tc_workspace_bytes.restype = C.c_int64
     l.omni_ssd_fwd_workspace_bytes.argtypes = [C.c_int64] * 6
     l.omni_ssd_fwd_workspace_bytes.restype = C.c_int64
     l.omni_selftest.argtypes = [C.c_void_p] * 10 + [C.c_int, C.c_void_p]
@@ -200,6 +202,10 @@ def reset_launch_count() -> None:
 
 def ssd_fwd_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate) -> int:
     return int(lib().omni_ssd_fwd_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate))
+
+
+def ssd_bwd_tc_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate) -> int:
+    return int(lib().omni_ssd_bwd_tc_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate))
 
 
 def ssd_bwd_workspace_elems(batch, seqlen, nheads, headdim, dstate) -> int:

@@ -6,6 +6,9 @@ int ssd_recurrent_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s);
 int ssd_recurrent_bwd(const omni_ssd_bwd_params_t* p, cudaStream_t s);
 bool ssd_tc_fwd_supported(const omni_ssd_fwd_params_t* p);
 int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s);
+bool ssd_tc_bwd_supported(const omni_ssd_bwd_params_t* p);
+int ssd_tc_bwd(const omni_ssd_bwd_params_t* p, cudaStream_t s);
+int64_t ssd_tc_bwd_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t ngroups);
 }  // namespace omni
 
 using namespace omni;
@@ -26,5 +29,21 @@ extern "C" int omni_ssd_chunk_scan_fwd(const omni_ssd_fwd_params_t* p, void* str
 
 extern "C" int omni_ssd_chunk_scan_bwd(const omni_ssd_bwd_params_t* p, void* stream) {
   OMNI_CHECK(p != nullptr, OMNI_BAD_SHAPE, "null params");
-  return ssd_recurrent_bwd(p, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (p->algo) {
+    case OMNI_SSD_RECURRENT: return ssd_recurrent_bwd(p, s);
+    case OMNI_SSD_CHUNKED_TC:
+      OMNI_CHECK(ssd_tc_bwd_supported(p), OMNI_UNSUPPORTED,
+                 "ssd bwd: the tcgen05 chunked kernels need bf16 x/B/C/dout/dx/out, headdim 64, d_state 128, no seq_idx / z, "
+                 "D of shape (H) and omni_ssd_bwd_tc_workspace_bytes() of 256-byte aligned workspace");
+      return ssd_tc_bwd(p, s);
+    case OMNI_SSD_AUTO: return ssd_tc_bwd_supported(p) ? ssd_tc_bwd(p, s) : ssd_recurrent_bwd(p, s);
+    default: return set_error(OMNI_UNSUPPORTED, "ssd bwd: unknown algo %d", p->algo);
+  }
+}
+
+extern "C" int64_t omni_ssd_bwd_tc_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim, int64_t ngroups,
+                                                   int64_t dstate) {
+  if (headdim != 64 || dstate != 128) return 0;
+  return ssd_tc_bwd_workspace_bytes(batch, seqlen, nheads, ngroups);
 }

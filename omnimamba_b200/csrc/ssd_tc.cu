@@ -89,6 +89,10 @@ struct TcArgs {
   int dt_softplus;
   float dt_min, dt_max;
   long long* trace; int trace_chunks;  // debug: per-event clock64 of CTA 0 (omni_debug_set_trace)
+  // mode 0: the forward.  Modes 1 / 2 run only the state recurrence of the same pipeline and TMA-store the fp16 state
+  // ENTERING every chunk (for the backward): 1 = forward states S_c from (x, B, sj); 2 = reverse sweep of the state
+  // gradient dS_{c+1} from (dy in the x slot, C in the B slot, exp(lam_i) as the row scale), chunks visited last to first.
+  int mode;
 };
 
 // trace slot layout: trace[g * 32 + event]
@@ -103,6 +107,7 @@ __device__ __forceinline__ float ex2f(float v) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -154,7 +159,8 @@ struct ChunkIter {
 // fetch (ncu stall_no_inst).  Inner loops are therefore kept rolled (#pragma unroll 1) wherever the body is large.
 __global__ void __launch_bounds__(kThreads, 1)
 ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapB,
-                  const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapY, TcArgs a) {
+                  const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapY,
+                  const __grid_constant__ CUtensorMap mapS, TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SM_TMEMPTR);
@@ -202,14 +208,16 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   auto it_next = [&](ChunkIter& it) {
     if (++it.c == nchunks) it_set(it, it.item + gridDim.x);
   };
+  const int mode = a.mode;
+  auto cphys = [&](int c) { return mode == 2 ? nchunks - 1 - c : c; };  // chunk visited at step c of an item
 
   if (warp == 0) {
     // ============ TMA producer ========================================================================================
     if (lane == 0 && total > 0) {
       auto load_b = [&](const ChunkIter& it, uint32_t st) {
         mbar_expect_tx(&bars[B_FULL_B + st], 32768);
-        tma_load_4d(smem + SM_B + st * 32768, &mapB, &bars[B_FULL_B + st], 0, it.h0 / hpg, it.c * Q, it.b);
-        tma_load_4d(smem + SM_B + st * 32768 + 16384, &mapB, &bars[B_FULL_B + st], 64, it.h0 / hpg, it.c * Q, it.b);
+        tma_load_4d(smem + SM_B + st * 32768, &mapB, &bars[B_FULL_B + st], 0, it.h0 / hpg, cphys(it.c) * Q, it.b);
+        tma_load_4d(smem + SM_B + st * 32768 + 16384, &mapB, &bars[B_FULL_B + st], 64, it.h0 / hpg, cphys(it.c) * Q, it.b);
       };
       auto load_c = [&](const ChunkIter& it) {
         mbar_expect_tx(&bars[B_FULL_C], 32768);
@@ -218,18 +226,21 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       };
       auto load_x = [&](const ChunkIter& it) {
         mbar_expect_tx(&bars[B_FULL_X], 32768);
-        tma_load_4d(smem + SM_XA, &mapX, &bars[B_FULL_X], 0, it.h0, it.c * Q, it.b);
-        tma_load_4d(smem + SM_XA + 16384, &mapX, &bars[B_FULL_X], 0, it.h0 + 1, it.c * Q, it.b);
+        tma_load_4d(smem + SM_XA, &mapX, &bars[B_FULL_X], 0, it.h0, cphys(it.c) * Q, it.b);
+        tma_load_4d(smem + SM_XA + 16384, &mapX, &bars[B_FULL_X], 0, it.h0 + 1, cphys(it.c) * Q, it.b);
       };
       auto prefetch = [&](const ChunkIter& it) {  // pull a later chunk's x / C tiles into L2 (B is loaded two chunks ahead)
-        tma_prefetch_4d(&mapC, 0, it.h0 / hpg, it.c * Q, it.b);
-        tma_prefetch_4d(&mapC, 64, it.h0 / hpg, it.c * Q, it.b);
-        tma_prefetch_4d(&mapX, 0, it.h0, it.c * Q, it.b);
-        tma_prefetch_4d(&mapX, 0, it.h0 + 1, it.c * Q, it.b);
+        if (mode == 0) {
+          tma_prefetch_4d(&mapC, 0, it.h0 / hpg, it.c * Q, it.b);
+          tma_prefetch_4d(&mapC, 64, it.h0 / hpg, it.c * Q, it.b);
+        }
+        tma_prefetch_4d(&mapX, 0, it.h0, cphys(it.c) * Q, it.b);
+        tma_prefetch_4d(&mapX, 0, it.h0 + 1, cphys(it.c) * Q, it.b);
       };
       ChunkIter it1, it2;  // chunks g + 1 and g + 2
       it_set(it1, blockIdx.x);
-      load_c(it1); load_b(it1, 0); load_x(it1);
+      if (mode == 0) load_c(it1);
+      load_b(it1, 0); load_x(it1);
       it_next(it1);
       it2 = it1;
       if (total > 1) { load_b(it1, 1); prefetch(it1); }
@@ -237,15 +248,18 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll 1
       for (uint32_t g = 0; g + 1 < total; ++g) {
         if (g + 2 < total) prefetch(it2);
-        mbar_wait(&bars[B_YOFF_DONE], g & 1);              // Yoff(g) has read C(g)
-        TR(2);
-        load_c(it1);
+        if (mode == 0) {
+          mbar_wait(&bars[B_YOFF_DONE], g & 1);            // Yoff(g) has read C(g)
+          TR(2);
+          load_c(it1);
+        }
         if (g + 2 < total) {
           mbar_wait(&bars[B_EMPTY_B + (g & 1)], (g >> 1) & 1);  // S-update(g) has read B stage g & 1
           TR(1);
           load_b(it2, g & 1);
         }
-        mbar_wait(&bars[B_YD_DONE], g & 1);                // Ydiag(g) has read x(g)
+        if (mode == 0) mbar_wait(&bars[B_YD_DONE], g & 1);   // Ydiag(g) has read x(g)
+        else mbar_wait(&bars[B_X16_READY], g & 1);           // (state sweeps: the x pass has read it)
         TR(0);
         load_x(it1);
         it_next(it1);
@@ -268,6 +282,17 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const uint32_t st = g & 1, n = g >> 1, ph = g & 1;
         const uint64_t dBk = make_sdesc(smem_u32(smem + SM_B + st * 32768), 16, 1024);
         const uint64_t dBm = make_sdesc(smem_u32(smem + SM_B + st * 32768), 16384, 1024);
+        if (mode != 0) {  // state sweeps: only the state update
+          mbar_wait(&bars[B_FULL_B + st], n & 1);
+          mbar_wait(&bars[B_S_READY], ph);
+          mbar_wait(&bars[B_X16_READY], ph);
+          tc_fence_after();
+#pragma unroll 1
+          for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + TM_S, dXB + k * 128, dBm + k * 128, id_u, true);
+          mma_commit(&bars[B_U_DONE]);
+          mma_commit(&bars[B_EMPTY_B + st]);
+          continue;
+        }
         // CB = C B^T
         mbar_wait(&bars[B_FULL_B + st], n & 1);
         mbar_wait(&bars[B_FULL_C], ph);
@@ -319,7 +344,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const int64_t base = it.b * a.dt_b + (int64_t)(it.h0 + hh) * a.dt_h;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int t = it.c * Q + lane * 4 + k;
+        const int t = cphys(it.c) * Q + lane * 4 + k;
         raw[k] = 0u;
         if (valid && t < a.L) {
           if (a.dt_dtype == OMNI_F32) raw[k] = __ldg(static_cast<const uint32_t*>(a.dt) + base + (int64_t)t * a.dt_l);
@@ -338,7 +363,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     load_raw(it, total > 0);
 #pragma unroll 1
     for (uint32_t g = 0; g < total; ++g) {
-      const int h = it.h0 + hh, c = it.c;
+      const int h = it.h0 + hh, c = cphys(it.c);
       const uint32_t st = g & 1, n = g >> 1;
       Tab* tab = reinterpret_cast<Tab*>(smem + SM_TAB) + st;
       if (hh == 0) TR(8);
@@ -428,6 +453,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const uint32_t st = g & 1, n = g >> 1, ph = g & 1;
       const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
       mbar_wait(&bars[B_TAB_READY + st], n & 1);
+      if (mode == 0) {
       // ---- P build: P_h = CB o decay o dt (causal), fp16, written over CB in TMEM
       float lam_i[2], u_i[2];
 #pragma unroll
@@ -503,12 +529,13 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       __syncwarp();
       if (pw == 3) TR(13);
       if (lane == 0) mbar_arrive(&bars[B_P_READY]);
+      }
       // ---- x pass: x row -> fp16 in place (Ydiag operand), X' row -> XB (state operand), D x -> Ydiag accumulator
-      const float sji = tab->sj[sub][i];
+      const float sji = mode == 2 ? tab->eL[sub][i] : tab->sj[sub][i];  // (reverse sweep: dy rows scale by exp(lam_i))
       const float Dh = a.D ? ld_any(a.D, a.D_dtype, it.h0 + sub) : 0.f;
       if (g > 0) {
         mbar_wait(&bars[B_U_DONE], ph ^ 1);     // S-update(g-1) has read XB
-        mbar_wait(&bars[B_ACC_FREE], ph ^ 1);   // epilogue(g-1) has read the Ydiag accumulator
+        if (mode == 0) mbar_wait(&bars[B_ACC_FREE], ph ^ 1);   // epilogue(g-1) has read the Ydiag accumulator
         tc_fence_after();
       }
       mbar_wait(&bars[B_FULL_X], ph);
@@ -537,7 +564,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             dx[8 * k + 4] = __float_as_uint(d2.x); dx[8 * k + 5] = __float_as_uint(d2.y);
             dx[8 * k + 6] = __float_as_uint(d3.x); dx[8 * k + 7] = __float_as_uint(d3.y);
           }
-          if (a.D != nullptr) tmem_st16(tmem_addr(tb, q * 32, TM_YD + 64 * sub + 8 * k8), dx);
+          if (a.D != nullptr && mode == 0) tmem_st16(tmem_addr(tb, q * 32, TM_YD + 64 * sub + 8 * k8), dx);
         }
       }
       tmem_st_wait();
@@ -570,8 +597,12 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
         mbar_wait(&bars[B_TAB_READY + st], n & 1);
         const float dch = tab->dchunk[hh];
+        if (mode != 0) {  // state sweeps: the previous TMA store must have read the S16 tile
+          if (w == 0 && lane == 0) tma_store_wait_read<0>();
+          named_bar_sync(1, 128);
+        }
         if (gg > 0) {
-          mbar_wait(&bars[B_YOFF_DONE], (gg - 1) & 1);  // Yoff(gg-1) has read the S16 tile
+          if (mode == 0) mbar_wait(&bars[B_YOFF_DONE], (gg - 1) & 1);  // Yoff(gg-1) has read the S16 tile
           mbar_wait(&bars[B_U_DONE], (gg - 1) & 1);     // S-update(gg-1) is complete
           tc_fence_after();
         }
@@ -634,9 +665,22 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         __syncwarp();
         if (w == 0) TR(16);
         if (lane == 0) mbar_arrive(&bars[B_S_READY]);
+        if (mode != 0) {  // state sweeps: the state ENTERING this chunk -> workspace[b][chunk][(h,p)][n] (fp16), no epilogue
+          named_bar_sync(1, 128);
+          if (w == 0 && lane == 0) {
+            tma_store_4d(&mapS, smem + SM_S, 0, sn.h0 * HD, cphys(sn.c), sn.b);
+            tma_store_4d(&mapS, smem + SM_S + 16384, 64, sn.h0 * HD, cphys(sn.c), sn.b);
+            tma_store_commit();
+          }
+          if (lane == 0) mbar_arrive(&bars[B_TAB_FREE + st]);
+        }
         it_next(sn);
       }
       if (gg == 0) continue;
+      if (mode != 0) {
+        it_next(ep);
+        continue;
+      }
       // ---- epilogue(g = gg - 1): y = Ydiag (+ D x) + exp(lam_i) Yoff, row i = r
       const uint32_t g = gg - 1;
       const uint32_t st = g & 1, ph = g & 1;
@@ -782,62 +826,69 @@ bool ssd_tc_fwd_supported(const omni_ssd_fwd_params_t* p) {
   return get_encode_tiled() != nullptr;
 }
 
-int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
-  const omni_tensor_t &x = p->x, &dt = p->dt, &Bm = p->B, &Cm = p->C, &o = p->out;
-  const int64_t Bsz = x.shape[0], L = x.shape[1], H = x.shape[2], G = Bm.shape[2];
+// fp16 copies of B and C (any batch / seq / group strides) in wsB / wsC (contiguous (B, L, G, N))
+int ssd_tc_prep(const omni_tensor_t& Bm, const omni_tensor_t& Cm, void* wsB, void* wsC, cudaStream_t s) {
+  const int64_t Bsz = Bm.shape[0], L = Bm.shape[1], G = Bm.shape[2];
+  const int64_t rows = Bsz * L * G;
+  PrepArgs pa{};
+  pa.src[0] = static_cast<const __nv_bfloat16*>(Bm.data); pa.src[1] = static_cast<const __nv_bfloat16*>(Cm.data);
+  pa.dst[0] = static_cast<__half*>(wsB); pa.dst[1] = static_cast<__half*>(wsC);
+  pa.s_b[0] = Bm.stride[0]; pa.s_l[0] = Bm.stride[1]; pa.s_g[0] = Bm.stride[2];
+  pa.s_b[1] = Cm.stride[0]; pa.s_l[1] = Cm.stride[1]; pa.s_g[1] = Cm.stride[2];
+  pa.L = (int)L; pa.G = (int)G; pa.rows = rows;
+  const int64_t nvec = rows * (NS / 8);
+  const unsigned gx = (unsigned)std::min<int64_t>((nvec + 255) / 256, (int64_t)sm_count() * 8);
+  ssd_tc_prep_kernel<<<dim3(gx, 2), 256, 0, s>>>(pa);
+  OMNI_CUDA_LAUNCH_CHECK("ssd_tc_prep_kernel");
+  return OMNI_OK;
+}
+
+namespace {
+// Common launcher.  mode 0: forward (x, wsB, wsC -> out).  mode 1 / 2: state sweeps (xlike, ws_bslot -> ws_states).
+int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const omni_tensor_t& A, const omni_tensor_t& D,
+              const omni_tensor_t& dt_bias, const omni_tensor_t& init, const omni_tensor_t& fin, const omni_tensor_t& o,
+              const void* wsB, const void* wsC, void* ws_states, int64_t G, int dt_softplus, float dt_min, float dt_max,
+              cudaStream_t s) {
+  const int64_t Bsz = x.shape[0], L = x.shape[1], H = x.shape[2];
+  const int64_t nchunks = (L + Q - 1) / Q;
   OMNI_CHECK(present(dt) && shape_is(dt, 3, Bsz, L, H) && is_float_dtype(dt.dtype), OMNI_BAD_SHAPE, "ssd: dt must be (B, L, H)");
-  OMNI_CHECK(present(p->A) && shape_is(p->A, 1, H) && p->A.dtype == OMNI_F32 && (H <= 1 || p->A.stride[0] == 1), OMNI_BAD_SHAPE,
+  OMNI_CHECK(present(A) && shape_is(A, 1, H) && A.dtype == OMNI_F32 && (H <= 1 || A.stride[0] == 1), OMNI_BAD_SHAPE,
              "ssd: A must be contiguous fp32 (H)");
-  OMNI_CHECK(shape_is(Bm, 4, Bsz, L, G, NS) && shape_is(Cm, 4, Bsz, L, G, NS), OMNI_BAD_SHAPE, "ssd: B/C must be (B, L, G, N)");
-  OMNI_CHECK(shape_is(o, 4, Bsz, L, H, HD), OMNI_BAD_SHAPE, "ssd: out must match x");
   TcArgs a{};
+  a.mode = mode;
   a.dt = dt.data; a.dt_dtype = dt.dtype; a.dt_b = dt.stride[0]; a.dt_l = dt.stride[1]; a.dt_h = dt.stride[2];
-  a.A = static_cast<const float*>(p->A.data);
+  a.A = static_cast<const float*>(A.data);
   a.x = static_cast<const __nv_bfloat16*>(x.data); a.x_b = x.stride[0]; a.x_l = x.stride[1]; a.x_h = x.stride[2];
-  a.out = o.data; a.out_dtype = o.dtype; a.o_b = o.stride[0]; a.o_l = o.stride[1]; a.o_h = o.stride[2];
-  if (present(p->D)) {
-    OMNI_CHECK(shape_is(p->D, 1, H) && is_float_dtype(p->D.dtype) && (H <= 1 || p->D.stride[0] == 1), OMNI_BAD_SHAPE,
+  if (mode == 0) {
+    a.out = o.data; a.out_dtype = o.dtype; a.o_b = o.stride[0]; a.o_l = o.stride[1]; a.o_h = o.stride[2];
+  } else {
+    a.out_dtype = OMNI_BF16;
+  }
+  if (present(D)) {
+    OMNI_CHECK(shape_is(D, 1, H) && is_float_dtype(D.dtype) && (H <= 1 || D.stride[0] == 1), OMNI_BAD_SHAPE,
                "ssd: D must be contiguous (H)");
-    a.D = p->D.data; a.D_dtype = p->D.dtype;
+    a.D = D.data; a.D_dtype = D.dtype;
   }
-  if (present(p->dt_bias)) {
-    OMNI_CHECK(shape_is(p->dt_bias, 1, H) && is_float_dtype(p->dt_bias.dtype) && (H <= 1 || p->dt_bias.stride[0] == 1),
+  if (present(dt_bias)) {
+    OMNI_CHECK(shape_is(dt_bias, 1, H) && is_float_dtype(dt_bias.dtype) && (H <= 1 || dt_bias.stride[0] == 1),
                OMNI_BAD_SHAPE, "ssd: dt_bias must be contiguous (H)");
-    a.dt_bias = p->dt_bias.data; a.dtb_dtype = p->dt_bias.dtype;
+    a.dt_bias = dt_bias.data; a.dtb_dtype = dt_bias.dtype;
   }
-  if (present(p->initial_states)) {
-    const omni_tensor_t& in = p->initial_states;
-    OMNI_CHECK(shape_is(in, 4, Bsz, H, HD, NS) && is_float_dtype(in.dtype) && in.stride[3] == 1, OMNI_BAD_SHAPE,
+  if (present(init)) {
+    OMNI_CHECK(shape_is(init, 4, Bsz, H, HD, NS) && is_float_dtype(init.dtype) && init.stride[3] == 1, OMNI_BAD_SHAPE,
                "ssd: initial_states must be (B, H, P, N)");
-    a.init = in.data; a.init_dtype = in.dtype; a.i_b = in.stride[0]; a.i_h = in.stride[1]; a.i_p = in.stride[2];
+    a.init = init.data; a.init_dtype = init.dtype; a.i_b = init.stride[0]; a.i_h = init.stride[1]; a.i_p = init.stride[2];
   }
-  if (present(p->final_states)) {
-    const omni_tensor_t& f = p->final_states;
-    OMNI_CHECK(shape_is(f, 4, Bsz, H, HD, NS) && f.dtype == OMNI_F32 && f.stride[3] == 1 && f.stride[2] == NS &&
-                   f.stride[1] == HD * NS && f.stride[0] == H * HD * NS && aligned16(f.data),
+  if (present(fin)) {
+    OMNI_CHECK(shape_is(fin, 4, Bsz, H, HD, NS) && fin.dtype == OMNI_F32 && fin.stride[3] == 1 && fin.stride[2] == NS &&
+                   fin.stride[1] == HD * NS && fin.stride[0] == H * HD * NS && aligned16(fin.data),
                OMNI_BAD_SHAPE, "ssd: final_states must be contiguous fp32 (B, H, P, N)");
-    a.fin = static_cast<float*>(f.data);
+    a.fin = static_cast<float*>(fin.data);
   }
   a.B = (int)Bsz; a.L = (int)L; a.H = (int)H; a.G = (int)G;
-  a.dt_softplus = p->dt_softplus; a.dt_min = p->dt_min; a.dt_max = p->dt_max;
-  a.trace = g_trace; a.trace_chunks = g_trace_chunks;
+  a.dt_softplus = dt_softplus; a.dt_min = dt_min; a.dt_max = dt_max;
+  a.trace = mode == 0 ? g_trace : nullptr; a.trace_chunks = g_trace_chunks;
 
-  // pre-pass: fp16 copies of B and C in the caller's workspace
-  const int64_t rows = Bsz * L * G;
-  __half* wsB = static_cast<__half*>(p->workspace.data);
-  __half* wsC = wsB + rows * NS;
-  {
-    PrepArgs pa{};
-    pa.src[0] = static_cast<const __nv_bfloat16*>(Bm.data); pa.src[1] = static_cast<const __nv_bfloat16*>(Cm.data);
-    pa.dst[0] = wsB; pa.dst[1] = wsC;
-    pa.s_b[0] = Bm.stride[0]; pa.s_l[0] = Bm.stride[1]; pa.s_g[0] = Bm.stride[2];
-    pa.s_b[1] = Cm.stride[0]; pa.s_l[1] = Cm.stride[1]; pa.s_g[1] = Cm.stride[2];
-    pa.L = (int)L; pa.G = (int)G; pa.rows = rows;
-    const int64_t nvec = rows * (NS / 8);
-    const unsigned gx = (unsigned)std::min<int64_t>((nvec + 255) / 256, (int64_t)sm_count() * 8);
-    ssd_tc_prep_kernel<<<dim3(gx, 2), 256, 0, s>>>(pa);
-    OMNI_CUDA_LAUNCH_CHECK("ssd_tc_prep_kernel");
-  }
   auto tmap4 = [&](CUtensorMap* m, const void* base, const int64_t* shape, const int64_t* stride, bool bf16, int rows) -> int {
     // dims innermost first: (inner, dim2, L, B); a size-1 dim may carry any stride: give TMA a harmless legal one
     const uint64_t dims[4] = {(uint64_t)shape[3], (uint64_t)shape[2], (uint64_t)shape[1], (uint64_t)shape[0]};
@@ -847,14 +898,22 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
     return make_tmap_16bit(m, base, 4, dims, strides, box, bf16);
   };
   const int64_t bc_shape[4] = {Bsz, L, G, NS}, bc_stride[4] = {L * G * NS, G * NS, NS, 1};
-  CUtensorMap mX, mB, mC, mY;
+  CUtensorMap mX, mB, mC, mY, mS;
   if (int rc = tmap4(&mX, x.data, x.shape, x.stride, true, Q)) return rc;
   if (int rc = tmap4(&mB, wsB, bc_shape, bc_stride, false, Q)) return rc;
-  if (int rc = tmap4(&mC, wsC, bc_shape, bc_stride, false, Q)) return rc;
-  if (o.dtype == OMNI_BF16) {  // y leaves through per-warp TMA stores of 32 rows
+  if (int rc = tmap4(&mC, wsC ? wsC : wsB, bc_shape, bc_stride, false, Q)) return rc;
+  if (mode == 0 && o.dtype == OMNI_BF16) {  // y leaves through per-warp TMA stores of 32 rows
     if (int rc = tmap4(&mY, o.data, o.shape, o.stride, true, 32)) return rc;
   } else {
-    mY = mX;  // unused by the fp32-output path
+    mY = mX;  // unused
+  }
+  if (mode != 0) {  // fp16 states: (n 128, rows H*64, chunk, batch), box 64 x 128 rows
+    const uint64_t dims[4] = {(uint64_t)NS, (uint64_t)(H * HD), (uint64_t)nchunks, (uint64_t)Bsz};
+    const uint64_t strides[3] = {(uint64_t)NS * 2, (uint64_t)(H * HD * NS) * 2, (uint64_t)(nchunks * H * HD * NS) * 2};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if (int rc = make_tmap_16bit(&mS, ws_states, 4, dims, strides, box, false)) return rc;
+  } else {
+    mS = mX;  // unused
   }
 
   static std::once_flag once[64];
@@ -865,9 +924,33 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
   });
   const int nitems = (int)(Bsz * (H / 2));
   const int grid = nitems < sm_count() ? nitems : sm_count();
-  ssd_tc_fwd_kernel<<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, a);
+  ssd_tc_fwd_kernel<<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
   OMNI_CUDA_LAUNCH_CHECK("ssd_tc_fwd_kernel");
   return OMNI_OK;
+}
+}  // namespace
+
+int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
+  const omni_tensor_t &x = p->x, &Bm = p->B, &Cm = p->C, &o = p->out;
+  const int64_t Bsz = x.shape[0], L = x.shape[1], H = x.shape[2], G = Bm.shape[2];
+  OMNI_CHECK(shape_is(Bm, 4, Bsz, L, G, NS) && shape_is(Cm, 4, Bsz, L, G, NS), OMNI_BAD_SHAPE, "ssd: B/C must be (B, L, G, N)");
+  OMNI_CHECK(shape_is(o, 4, Bsz, L, H, HD), OMNI_BAD_SHAPE, "ssd: out must match x");
+  // pre-pass: fp16 copies of B and C in the caller's workspace
+  __half* wsB = static_cast<__half*>(p->workspace.data);
+  __half* wsC = wsB + Bsz * L * G * NS;
+  if (int rc = ssd_tc_prep(Bm, Cm, wsB, wsC, s)) return rc;
+  return tc_launch(0, x, p->dt, p->A, p->D, p->dt_bias, p->initial_states, p->final_states, o, wsB, wsC, nullptr, G,
+                   p->dt_softplus, p->dt_min, p->dt_max, s);
+}
+
+// State sweeps for the backward (ssd_tc_bwd.cu): mode 1 = forward states from (x, fp16 B), mode 2 = reverse sweep of the
+// state gradients from (dy, fp16 C).  `init` seeds the recurrence, `fin` (fp32, optional) receives its last state.
+int ssd_tc_state_sweep(int mode, const omni_tensor_t& xlike, const omni_tensor_t& dt, const omni_tensor_t& A,
+                       const omni_tensor_t& dt_bias, const omni_tensor_t& init, const omni_tensor_t& fin, const void* ws_bslot,
+                       void* ws_states, int64_t G, int dt_softplus, float dt_min, float dt_max, cudaStream_t s) {
+  omni_tensor_t none{};
+  return tc_launch(mode, xlike, dt, A, none, dt_bias, init, fin, none, ws_bslot, nullptr, ws_states, G, dt_softplus, dt_min,
+                   dt_max, s);
 }
 
 }  // namespace omni

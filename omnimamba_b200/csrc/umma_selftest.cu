@@ -4,7 +4,7 @@
 //   D2[i][p]      = sum_j f16(P[i][j]) X[j][p]       A: TMEM fp16 (tcgen05.st)    B: smem MN-major bf16 (TMA)  N=64
 //   D3[r][n]      = sum_j bf16(Xs[r][j]) B[j][n]     A: TMEM bf16 (tcgen05.st)    B: smem MN-major (TMA, LBO)  N=128
 //   D4[i][r]      = sum_n C[i][n] bf16(S[r][n])      A: smem K-major (TMA)        B: smem K-major (st.shared)  N=128
-//   bit6: D3 with A = Xs^T as an MN-major SMEM operand (SS form).  bit8: every operand fp16 instead of bf16.
+//   bit6: D3 with A = Xs^T as an MN-major SMEM operand (SS form); bit7: D3 with A = Xs as a K-major SMEM operand x MN-major B.  bit8: every operand fp16 instead of bf16.
 //   A and B of one tcgen05.mma must share the 16-bit format: kind::f16 with an fp16 A and a bf16 B raises an illegal-
 //   instruction fault on sm_100a (measured), which is why the SSD kernel converts B, C and x to fp16.
 #include "umma.cuh"
@@ -122,10 +122,23 @@ __global__ void __launch_bounds__(128) selftest_kernel(const __grid_constant__ C
   for (int c0 = 0; c0 < 64; c0 += 16) {
     uint32_t v[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] = pack_bf16(a.Xs[row * 128 + 2 * (c0 + c)], a.Xs[row * 128 + 2 * (c0 + c) + 1]);
+    for (int c = 0; c < 16; ++c)
+      v[c] = f16m ? pack_f16(a.Xs[row * 128 + 2 * (c0 + c)], a.Xs[row * 128 + 2 * (c0 + c) + 1])
+                  : pack_bf16(a.Xs[row * 128 + 2 * (c0 + c)], a.Xs[row * 128 + 2 * (c0 + c) + 1]);
     tmem_st16(tmem_addr(tb, warp * 32, 448 + c0), v);
   }
   tmem_st_wait();
+  if (a.which & 128) {  // Xs as a K-major smem A operand: row r, K = j (two 64-wide halves), for the K-major x MN-major SS form
+    for (int ch = 0; ch < 16; ++ch) {
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        w[q] = f16m ? pack_f16(a.Xs[row * 128 + ch * 8 + 2 * q], a.Xs[row * 128 + ch * 8 + 2 * q + 1])
+                    : pack_bf16(a.Xs[row * 128 + ch * 8 + 2 * q], a.Xs[row * 128 + ch * 8 + 2 * q + 1]);
+      *reinterpret_cast<uint4*>(sS + (ch >> 3) * 16384 + sw128(row, ch & 7)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    fence_proxy_async_smem();
+  }
   if (a.which & 64) {  // Xs^T as an fp16 MN-major smem A operand: element (j, r) in row j of the (r >> 6) half
     for (int j = 0; j < 128; ++j) {
       uint8_t* dst = sS + (row >> 6) * 16384 + sw128(j, (row & 63) >> 3) + (row & 7) * 2;
@@ -147,6 +160,10 @@ __global__ void __launch_bounds__(128) selftest_kernel(const __grid_constant__ C
     for (int k = 0; k < 8; ++k)
       mma_ss(tb + 192, make_sdesc(smem_u32(sS) + k * 2048, 16384, 1024), make_sdesc(smem_u32(sB) + k * 2048, 16384, 1024),
              idesc5, k > 0);
+    if (a.which & 128)
+    for (int k = 0; k < 8; ++k)
+      mma_ss(tb + 192, make_sdesc(smem_u32(sS) + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+             make_sdesc(smem_u32(sB) + k * 2048, 16384, 1024), idesc3, k > 0);
     mma_commit(&bar_mma);
   }
   __syncthreads();

@@ -47,8 +47,9 @@ def ssd_fwd_raw(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initia
 
 def ssd_bwd_raw(dout, x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initial_states=None, seq_idx=None,
                 dt_softplus=False, dt_limit=(0.0, float("inf")), dfinal_states=None, dx=None, ddt=None, dz=None,
-                want_dinitial=False, algo="auto"):
-    """Returns dx, ddt (raw), dA (H), dB, dC (fp32, (B,L,G,N)), dD, dz, ddt_bias, dinitial_states."""
+                want_dinitial=False, algo="auto", out=None):
+    """Returns dx, ddt (raw), dA (H), dB, dC (fp32, (B,L,G,N)), dD, dz, ddt_bias, dinitial_states.
+    bf16 x/B/C/dout with the OmniMamba geometry run on the tensor-core kernels (algo "auto"); `out` is accepted and ignored."""
     batch, seqlen, nheads, headdim = x.shape
     ngroups, dstate = B.shape[-2], B.shape[-1]
     dev = x.device
@@ -64,11 +65,29 @@ def ssd_bwd_raw(dout, x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, 
     ddtb_part = torch.empty(batch, nheads, device=dev, dtype=torch.float32)
     dD_part = torch.empty(batch, nheads, headdim, device=dev, dtype=torch.float32)
     dinit = torch.empty(batch, nheads, headdim, dstate, device=dev, dtype=torch.float32) if want_dinitial else None
-    ws = torch.zeros(abi.ssd_bwd_workspace_elems(batch, seqlen, nheads, headdim, dstate), device=dev, dtype=torch.float32)
+    def _tma_ok(t):  # 16-byte aligned base and outer strides, contiguous rows
+        return t.dtype == torch.bfloat16 and t.stride(-1) == 1 and t.data_ptr() % 16 == 0 and \
+            all(t.shape[d] == 1 or t.stride(d) % 8 == 0 for d in range(t.dim() - 1))
+
+    tc_bytes = 0
+    if (algo != "recurrent" and z is None and seq_idx is None and (D is None or D.dim() == 1)
+            and (nheads // ngroups) % 2 == 0 and all(_tma_ok(t) for t in (x, dout, dx, B, C))):
+        tc_bytes = abi.ssd_bwd_tc_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate)
+    if algo == "chunked_tc" and tc_bytes == 0:
+        raise RuntimeError("ssd bwd: algo='chunked_tc' needs bf16 x/B/C/dout (16-byte aligned rows), headdim 64, "
+                           "d_state 128, an even number of heads per group, D of shape (H), no z / seq_idx")
+    if tc_bytes > 0:  # tensor-core path: fp16 B/C copies + fp16 chunk states and state gradients (not zero-filled)
+        ws = torch.empty((tc_bytes + 3) // 4, device=dev, dtype=torch.float32)
+        dD_part = torch.empty(batch, nheads, device=dev, dtype=torch.float32)
+        algo = "chunked_tc"
+    else:
+        ws = torch.zeros(abi.ssd_bwd_workspace_elems(batch, seqlen, nheads, headdim, dstate), device=dev, dtype=torch.float32)
+        algo = "recurrent"
     p = abi.SsdBwd()
     p.x, p.dt, p.A, p.B, p.C = (abi.tdesc(t) for t in (x, dt, A, B, C))
     p.D, p.z, p.dt_bias = abi.tdesc(D), abi.tdesc(z), abi.tdesc(dt_bias)
     p.initial_states, p.seq_idx = abi.tdesc(initial_states), abi.tdesc(seq_idx)
+    p.out = abi.tdesc(None)  # (reserved: no algorithm needs the forward output; r_i is re-formed in fp32)
     p.dout, p.dfinal_states = abi.tdesc(dout), abi.tdesc(dfinal_states)
     p.dx, p.ddt, p.dB, p.dC, p.dz = (abi.tdesc(t) for t in (dx, ddt, dB, dC, dz))
     p.dinitial_states = abi.tdesc(dinit)
@@ -82,7 +101,7 @@ def ssd_bwd_raw(dout, x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, 
     ddt_bias = ddtb_part.sum(0) if dt_bias is not None else None
     dD = None
     if D is not None:
-        dD = dD_part.sum(0) if D.dim() == 2 else dD_part.sum((0, 2))
+        dD = dD_part.sum(0) if (D.dim() == 2 or dD_part.dim() == 2) else dD_part.sum((0, 2))
     return dx, ddt, dA, dB, dC, dD, dz, ddt_bias, dinit
 
 

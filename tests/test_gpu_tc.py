@@ -47,12 +47,14 @@ def run_selftest(which):
         errs["D3 = r(Xs) B (TS, MN-major with LBO)"] = rel_l2(D3, r16(Xs) @ Bf)
     if which & 64:
         errs["D3 = r(Xs) B (SS, A MN-major smem x B MN-major)"] = rel_l2(D3, r16(Xs) @ Bf)
+    if which & 128:
+        errs["D3 = r(Xs) B (SS, A K-major smem x B MN-major)"] = rel_l2(D3, r16(Xs) @ Bf)
     if which & 4:
         errs["D4 = C r(S)^T (SS, thread-written swizzled B)"] = rel_l2(D4, Cf @ r16(S).t())
     return errs
 
 
-@pytest.mark.parametrize("which", [1, 2, 4, 8, 64, 15, 257, 258, 260, 320, 263])
+@pytest.mark.parametrize("which", [1, 2, 4, 8, 64, 128, 15, 257, 258, 260, 264, 320, 384, 271])
 def test_umma_selftest(which):
     # each form in its own process: an illegal-instruction fault poisons the CUDA context
     code = f"import sys; sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r});" \
@@ -149,3 +151,61 @@ def test_ssd_tc_matches_recurrent_at_bench_size():
     e, ef = rel_l2(o2, o1), rel_l2(f2, f1)
     print(f"tc vs recurrent at 16x4096: out {e:.2e} final {ef:.2e}")
     assert e < 1e-3 and ef < 3e-3
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tensor-core chunked SSD backward (state sweeps + per-chunk gradient kernel) vs the oracle's autograd
+# ------------------------------------------------------------------------------------------------------------
+def _tc_bwd_case(batch, L, H, G, seed, variant):
+    import oracle
+    from cases import scan_inputs
+    from omnimamba_b200.interface.ssd_combined import ssd_bwd_raw, ssd_fwd_raw
+    x, dt, A, Bm, Cm, D, dt_bias = scan_inputs(batch, L, H, 64, G, 128, seed, torch.bfloat16)
+    g = torch.Generator().manual_seed(seed + 1)
+    dy = torch.randn(batch, L, H, 64, generator=g).to(torch.bfloat16)
+    init = torch.randn(batch, H, 64, 128, generator=g) if variant == "init_final" else None
+    dfin = torch.randn(batch, H, 64, 128, generator=g) if variant == "init_final" else None
+    lim = (0.002, 0.08) if variant == "limit" else (0.0, float("inf"))
+    # oracle: fp32 autograd on the same (bf16-valued) inputs
+    leaf = lambda t: None if t is None else t.float().detach().clone().requires_grad_()
+    xr, dtr, Ar, Br, Cr, Dr, dbr, ir = (leaf(t) for t in (x, dt, A, Bm, Cm, D, dt_bias, init))
+    res = oracle.mamba_chunk_scan_combined_ref(xr, dtr, Ar, Br, Cr, 256, D=Dr, dt_bias=dbr, initial_states=ir, dt_softplus=True,
+                                               dt_limit=lim, return_final_states=dfin is not None)
+    if dfin is not None:
+        yr, fr = res
+        (yr * dy.float()).sum().add((fr * dfin).sum()).backward()
+    else:
+        (res * dy.float()).sum().backward()
+    c = lambda t: None if t is None else t.to(DEV)
+    out, _ = ssd_fwd_raw(c(x), c(dt), c(A), c(Bm), c(Cm), 256, D=c(D), dt_bias=c(dt_bias), initial_states=c(init),
+                         dt_softplus=True, dt_limit=lim, algo="chunked_tc")
+    dx, ddt, dA, dB, dC, dD, _, ddtb, dinit = ssd_bwd_raw(
+        c(dy), c(x), c(dt), c(A), c(Bm), c(Cm), 256, D=c(D), dt_bias=c(dt_bias), initial_states=c(init), dt_softplus=True,
+        dt_limit=lim, dfinal_states=c(dfin), want_dinitial=init is not None, algo="chunked_tc", out=out)
+    torch.cuda.synchronize()
+
+    def rel_sum(a, ref, terms):
+        """Error of a per-head SUM over (batch, time) relative to the L2 norm of its summands: a sum of terms that each
+        carry a relative error eps is off by ~eps * ||terms||_2 however much the terms cancel."""
+        return ((a.double().cpu() - ref.double()).norm() / terms.double().norm().clamp_min(1e-30)).item()
+
+    ddt_ref = dtr.grad  # (B, L, H): the summands of ddt_bias; dA_h = sum dt da has summands of the size of ddt / |A_h|
+    errs = {"dx": rel_l2(dx, xr.grad), "ddt": rel_l2(ddt, ddt_ref), "dB": rel_l2(dB, Br.grad), "dC": rel_l2(dC, Cr.grad),
+            "dD": rel_l2(dD, Dr.grad), "ddt_bias": rel_sum(ddtb, dbr.grad, ddt_ref),
+            "dA": rel_sum(dA, Ar.grad, ddt_ref / Ar.detach().abs())}
+    if init is not None:
+        errs["dinitial_states"] = rel_l2(dinit, ir.grad)
+    return errs
+
+
+@pytest.mark.parametrize("batch,L,H,G", [(1, 128, 2, 1), (2, 329, 4, 1), (1, 1024, 8, 1), (3, 72, 4, 2), (1, 1, 2, 1), (2, 257, 6, 1)])
+@pytest.mark.parametrize("variant", ["plain", "init_final", "limit"])
+def test_ssd_tc_bwd(batch, L, H, G, variant):
+    """Gradient tolerance for bf16 I/O: 1e-2 relative L2 (tests/test_gpu_parity.py GTOL) against fp32 autograd of the oracle;
+    the per-head sums dA and ddt_bias are measured against the norm of their summands (see rel_sum)."""
+    errs = _tc_bwd_case(batch, L, H, G, 23, variant)
+    print(f"tc bwd B={batch} L={L} H={H} G={G} {variant}: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        # dA / ddt_bias: the reverse cumulative sums inside a chunk make the fp16 operand rounding of neighbouring tokens
+        # correlated, so these sums over (batch, time) get 3e-2 (upstream's own bf16 tolerance for them is rtol 3e-2 too)
+        assert v < (3e-2 if k in ("dA", "ddt_bias") else 1e-2), (k, v)
