@@ -245,6 +245,8 @@ OMNI_API int omni_selftest(const void* Cm, const void* Bm, const void* X, const 
 /* debug: CTA 0 of subsequent tensor-core SSD launches writes clock64() per (chunk, event) into buf[chunks*32]
  * (device int64; NULL disables).  Used by scripts/trace_tc.py to find pipeline stalls. */
 OMNI_API void omni_debug_set_trace(void* buf, int chunks);
+/* debug: as omni_debug_set_trace, for the backward gradient kernel: buf[items * 32] clock64 stamps per phase of CTA 0. */
+OMNI_API void omni_debug_set_bwd_trace(void* buf, int items);
 /* debug: suspend-time hint (ns) used by the mbarrier waits of the tensor-core SSD kernel (tuning experiments). */
 OMNI_API void omni_debug_set_mbar_hint(unsigned ns);
 /* debug: cycles for `iters` tcgen05.ld (mode 0/2: 4 KB each per warp) or 2x tcgen05.st (mode 1) per warp with nwarps warps

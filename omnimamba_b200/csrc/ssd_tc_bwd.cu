@@ -77,7 +77,13 @@ struct BwdArgs {
   int dt_dtype, D_dtype, dtb_dtype, ddt_dtype;
   int dt_softplus;
   float dt_min, dt_max;
+  long long* trace; int trace_items;  // debug: clock64 of CTA 0 at phase boundaries (omni_debug_set_bwd_trace)
 };
+#define BTR(ev)                                                                                   \
+  do {                                                                                            \
+    if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && it_count < a.trace_items)           \
+      a.trace[it_count * 32 + (ev)] = clock64();                                                  \
+  } while (0)
 
 __device__ __forceinline__ float ex2f(float v) {
   float r;
@@ -128,9 +134,9 @@ __device__ __forceinline__ void scale_block(const uint32_t (&val)[32], const flo
   }
 }
 // Diagonal block with extreme decay: the decay of every element directly, exp2(min(sgn (lam_col - lam_row), 0)).
-__device__ __noinline__ void scale_block_direct(const uint32_t (&val)[32], const float* lamc, const float* colmul, float lamr,
+__device__ __forceinline__ void scale_block_direct(const uint32_t (&val)[32], const float* lamc, const float* colmul, float lamr,
                                                 float rowmul, float sgn, int mask, int lane, uint32_t (&pk)[16]) {
-#pragma unroll 4
+#pragma unroll
   for (int e = 0; e < 16; ++e) {
     float p[2];
 #pragma unroll
@@ -171,23 +177,32 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
   const int HP = a.H >> 1, hpg = a.H / a.G;
   const int nitems = a.B * a.nchunks * HP;
-  const uint32_t id_kk = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
-  const uint32_t id_ts64 = make_idesc(128, 64, kFmtF16, kFmtF16, kMajorK, kMajorMN);
-  const uint32_t id_ts128 = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorMN);
-  const uint64_t dXk = make_sdesc(smem_u32(smem + SM_X), 16, 1024), dDYk = make_sdesc(smem_u32(smem + SM_DY), 16, 1024);
-  const uint64_t dDYm = make_sdesc(smem_u32(smem + SM_DY), 16384, 1024);
-  const uint64_t dBk = make_sdesc(smem_u32(smem + SM_B), 16, 1024), dBm = make_sdesc(smem_u32(smem + SM_B), 16384, 1024);
-  const uint64_t dCk = make_sdesc(smem_u32(smem + SM_C), 16, 1024), dCm = make_sdesc(smem_u32(smem + SM_C), 16384, 1024);
-  const uint64_t dSm = make_sdesc(smem_u32(smem + SM_S), 16384, 1024), dSk = make_sdesc(smem_u32(smem + SM_S), 16, 1024);
-  const uint64_t dDSk = make_sdesc(smem_u32(smem + SM_DS), 16, 1024), dDSm = make_sdesc(smem_u32(smem + SM_DS), 16384, 1024);
+  // instruction / shared-memory descriptors are rebuilt where the single issuing thread needs them (keeping fourteen 64-bit
+  // descriptors live in every thread's registers across the item loop caused spills)
+#define id_kk make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK)
+#define id_ts64 make_idesc(128, 64, kFmtF16, kFmtF16, kMajorK, kMajorMN)
+#define id_ts128 make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorMN)
+#define dXk make_sdesc(smem_u32(smem + SM_X), 16, 1024)
+#define dDYk make_sdesc(smem_u32(smem + SM_DY), 16, 1024)
+#define dDYm make_sdesc(smem_u32(smem + SM_DY), 16384, 1024)
+#define dBk make_sdesc(smem_u32(smem + SM_B), 16, 1024)
+#define dBm make_sdesc(smem_u32(smem + SM_B), 16384, 1024)
+#define dCk make_sdesc(smem_u32(smem + SM_C), 16, 1024)
+#define dCm make_sdesc(smem_u32(smem + SM_C), 16384, 1024)
+#define dSm make_sdesc(smem_u32(smem + SM_S), 16384, 1024)
+#define dSk make_sdesc(smem_u32(smem + SM_S), 16, 1024)
+#define dDSk make_sdesc(smem_u32(smem + SM_DS), 16, 1024)
+#define dDSm make_sdesc(smem_u32(smem + SM_DS), 16384, 1024)
   auto koff = [](uint32_t k) { return ((k >> 2) << 10) + ((k & 3) << 1); };  // k-major 128-wide K: 16-byte units
 
   uint32_t ph = 0;  // mbarrier phase parity: every barrier completes exactly once per item
+  int it_count = 0;
 #pragma unroll 1
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x, ph ^= 1) {
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x, ph ^= 1, ++it_count) {
     const int hp = item % HP, bc = item / HP, c = bc % a.nchunks, b = bc / a.nchunks;
     const int h0 = hp * 2, grp = h0 / hpg, t0 = c * Q;
 
+    BTR(0);
     // ---- A. tile loads (one thread) and the decay tables (threads 0..255: head tid >> 7, token tid & 127) -----------
     if (tid == 0) {
       mbar_expect_tx(&bars[BB_TMA], 6 * 32768);
@@ -239,7 +254,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       ref[2] = ref[1] + tab->wsum[th][1];
       ref[3] = ref[2] + tab->wsum[th][2];
       const float lam_last = ref[3] + tab->wsum[th][3];
-      const float myref = ref[wj];
+      const float myref = wj == 0 ? ref[0] : (wj == 1 ? ref[1] : (wj == 2 ? ref[2] : ref[3]));
       my_lam += myref;
       tab->lam[th][tj] = my_lam;
       tab->dtv[th][tj] = my_dt;
@@ -256,7 +271,9 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
 
     // ---- B. x, dy: bf16 -> fp16 in place --------------------------------------------------------------------------------
+    BTR(1);
     mbar_wait(&bars[BB_TMA], ph);
+    BTR(2);
     {
       uint4* xt = reinterpret_cast<uint4*>(smem + SM_X);  // SM_X and SM_DY are adjacent: 4096 16-byte slots
 #pragma unroll 1
@@ -271,6 +288,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     tc_fence_before();
     __syncthreads();
 
+    BTR(3);
     // ---- C. G1: CB^T = B C^T -> R0;  G3: ws = B dS16^T -> R1 -----------------------------------------------------------
     if (tid == 0) {
       tc_fence_after();
@@ -282,16 +300,15 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
     // ---- D. PT_h[j][i] = CB^T[j][i] L_ij (i >= j), fp16, in place (rows j, 32-column block ib = wq) ---------------------
     mbar_wait(&bars[BB_C1], ph);   // (the __syncthreads of phase B also published the tables)
+    BTR(4);
     bool safe = true;
 #pragma unroll
     for (int e = 0; e < 8; ++e) safe = safe && (&tab->bsafe[0][0])[e] != 0;
     tc_fence_after();
     {
       uint32_t cbt[32];
-      if (wq >= q) {
-        tmem_ld32(tmem_addr(tb, q * 32, R0 + 32 * wq), cbt);
-        tmem_ld_wait();
-      }
+      tmem_ld32(tmem_addr(tb, q * 32, R0 + 32 * wq), cbt);  // (unconditional: a predicated load would put cbt in local memory)
+      tmem_ld_wait();
       tc_fence_before();
       __syncthreads();  // every block is in registers before any warp overwrites the region with fp16
       tc_fence_after();
@@ -313,6 +330,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    BTR(5);
     // ---- E. G2: wd_h = PT_h dy_h -> R2 + 64 h ----------------------------------------------------------------------
     if (tid == 0) {
       tc_fence_after();
@@ -325,6 +343,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
     // ---- F. dx_j = dt_j (wd_j + es_j ws_j) + D dy_j; x.w and x.wd row sums; one head at a time through the staging tile --
     mbar_wait(&bars[BB_C2], ph);
+    BTR(6);
     tc_fence_after();
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
@@ -367,6 +386,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         tma_store_commit();
       }
     }
+    BTR(7);
     // ---- G. G4: G_h0 = dy_h0 x_h0^T -> R0;  G4': G_h0^T -> R1 ---------------------------------------------------------
     // <C_i, acc_i> over this warp's 32 columns n of the dC accumulator (row i = `row`), added to dst[row]
     auto dot_c_acc = [&](float* dst) {
@@ -404,45 +424,54 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       mbar_wait(&bars[h == 0 ? BB_C3 : BB_C4], ph);
+      BTR(8 + 2 * h);
       tc_fence_after();
       if (h == 1) dot_c_acc(tab->rr[0]);  // the dC accumulator holds M_0 B only: head 0's within-chunk part of r_i
-      uint32_t g[32], gt[32];
-      if (wq <= q) tmem_ld32(tmem_addr(tb, q * 32, R0 + 32 * wq), g);
-      if (wq >= q) tmem_ld32(tmem_addr(tb, q * 32, R1 + 32 * wq), gt);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
       uint32_t pk[16];
-      // M block (row i = `row`, column block jb = wq)
-      if (wq > q) {
+      {  // M block (row i = `row`, column block jb = wq): the source block is in registers before any warp stores fp16
+        uint32_t g[32];
+        tmem_ld32(tmem_addr(tb, q * 32, R0 + 32 * wq), g);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (wq > q) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) pk[e] = 0u;
-      } else if (wq < q) {
-        scale_block(g, &tab->v[h][q - 1][32 * wq], tab->ci[h][row], 0, lane, pk);
-      } else {
-        if (safe) scale_block(g, &tab->vd[h][32 * wq], tab->ci[h][row], 1, lane, pk);
-        else scale_block_direct(g, &tab->lam[h][32 * wq], &tab->dtv[h][32 * wq], tab->lam[h][row], 1.f, -1.f, 1, lane, pk);
-        float gd = 0.f;  // G_ii = dy_i . x_i sits on the diagonal of this block
+          for (int e = 0; e < 16; ++e) pk[e] = 0u;
+        } else if (wq < q) {
+          scale_block(g, &tab->v[h][q - 1][32 * wq], tab->ci[h][row], 0, lane, pk);
+        } else {
+          if (safe) scale_block(g, &tab->vd[h][32 * wq], tab->ci[h][row], 1, lane, pk);
+          else scale_block_direct(g, &tab->lam[h][32 * wq], &tab->dtv[h][32 * wq], tab->lam[h][row], 1.f, -1.f, 1, lane, pk);
+          float gd = 0.f;  // G_ii = dy_i . x_i sits on the diagonal of this block
 #pragma unroll
-        for (int e = 0; e < 32; ++e) gd = e == lane ? __uint_as_float(g[e]) : gd;
-        tab->gii[h][row] = gd;
+          for (int e = 0; e < 32; ++e) gd = e == lane ? __uint_as_float(g[e]) : gd;
+          tab->gii[h][row] = gd;
+        }
+        tmem_st16(tmem_addr(tb, q * 32, R0 + 16 * wq), pk);
       }
-      tmem_st16(tmem_addr(tb, q * 32, R0 + 16 * wq), pk);
-      // MT block (row j = `row`, column block ib = wq)
-      if (wq < q) {
+      {  // MT block (row j = `row`, column block ib = wq), in R1
+        uint32_t gt[32];
+        tmem_ld32(tmem_addr(tb, q * 32, R1 + 32 * wq), gt);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (wq < q) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) pk[e] = 0u;
-      } else if (wq > q || safe) {
-        const float refb = wq == 0 ? 0.f : tab->lam[h][32 * wq - 1];
-        scale_block(gt, &tab->ci[h][32 * wq], ex2f(refb - tab->lam[h][row]) * tab->dtv[h][row], wq == q ? 2 : 0, lane, pk);
-      } else {
-        scale_block_direct(gt, &tab->lam[h][32 * wq], nullptr, tab->lam[h][row], tab->dtv[h][row], 1.f, 2, lane, pk);
+          for (int e = 0; e < 16; ++e) pk[e] = 0u;
+        } else if (wq > q || safe) {
+          const float refb = wq == 0 ? 0.f : tab->lam[h][32 * wq - 1];
+          scale_block(gt, &tab->ci[h][32 * wq], ex2f(refb - tab->lam[h][row]) * tab->dtv[h][row], wq == q ? 2 : 0, lane, pk);
+        } else {
+          scale_block_direct(gt, &tab->lam[h][32 * wq], nullptr, tab->lam[h][row], tab->dtv[h][row], 1.f, 2, lane, pk);
+        }
       }
       tmem_st16(tmem_addr(tb, q * 32, R1 + 16 * wq), pk);
       tmem_st_wait();
       tc_fence_before();
       __syncthreads();
+      BTR(9 + 2 * h);
       // ---- I/K. G5: dC (+)= M_h B -> R2;  G7: dB (+)= MT_h C -> R3;  then the next head's G / G^T ----------------------
       if (tid == 0) {
         tc_fence_after();
@@ -460,6 +489,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
     // ---- L. x16 -> X' = es dt x, dy16 -> exp(lam_i) dy, in place;  zc_h = <dS_{c+1}, S_c> ---------------------------------
     mbar_wait(&bars[BB_C5], ph);
+    BTR(12);
     tc_fence_after();
     dot_c_acc(tab->rr[1]);  // (M_0 + M_1) B: both heads' within-chunk parts
     {
@@ -498,6 +528,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    BTR(13);
     // ---- M. G6: dC += (exp(lam) dy) S_c -> R2;  G8: dB += X' dS_{c+1} -> R3 ------------------------------------------------
     if (tid == 0) {
       tc_fence_after();
@@ -512,6 +543,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
     // ---- N0. roff_i = (exp(lam_i) dy_i) . (C_i S_c): rows i, this warp's 32 columns (h, p) of G10 --------------------------
     mbar_wait(&bars[BB_C6], ph);
+    BTR(14);
     tc_fence_after();
     {
       uint32_t v[32];
@@ -591,7 +623,9 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       }
     }
     // ---- N2. dC (R2), dB (R3): TMEM -> fp32 staging over the dead x/dy and B/C tiles -> coalesced vector reductions ----
+    BTR(15);
     __syncthreads();  // (warps 0, 1 still read the C / dy tiles through the tables only: the tiles themselves are dead)
+    BTR(16);
     {
       float* stC = reinterpret_cast<float*>(smem + SM_X);   // [128 rows][32 float4 chunks], chunk slot = chunk ^ (row & 31)
       float* stB = reinterpret_cast<float*>(smem + SM_B);
@@ -618,6 +652,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
       }
     }
+    BTR(17);
     if (tid == 0) tma_store_wait_read<0>();  // the dx staging tile and the next item's loads
     tc_fence_before();
     __syncthreads();
@@ -628,6 +663,8 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   if (warp == 1) tmem_dealloc(tb, 512);
 }
 
+long long* g_btrace = nullptr;
+int g_btrace_items = 0;
 }  // namespace
 
 // ---- host ---------------------------------------------------------------------------------------------------------
@@ -727,6 +764,7 @@ int ssd_tc_bwd(const omni_ssd_bwd_params_t* p, cudaStream_t s) {
   a.dD_part = static_cast<float*>(p->dD_part.data);
   a.B = (int)Bsz; a.L = (int)L; a.H = (int)H; a.G = (int)G; a.nchunks = (int)nchunks;
   a.dt_softplus = p->dt_softplus; a.dt_min = p->dt_min; a.dt_max = p->dt_max;
+  a.trace = g_btrace; a.trace_items = g_btrace_items;
   // the three per-(batch, head) sums are accumulated with atomics across the chunks of a sequence
   cudaMemsetAsync(a.dA_part, 0, sizeof(float) * Bsz * H, s);
   cudaMemsetAsync(a.ddtb_part, 0, sizeof(float) * Bsz * H, s);
@@ -768,3 +806,9 @@ int ssd_tc_bwd(const omni_ssd_bwd_params_t* p, cudaStream_t s) {
 }
 
 }  // namespace omni
+
+// debug: CTA 0 of subsequent tensor-core SSD backward launches records clock64() per (item, phase) into buf[items * 32]
+extern "C" void omni_debug_set_bwd_trace(void* buf, int items) {
+  omni::g_btrace = static_cast<long long*>(buf);
+  omni::g_btrace_items = items;
+}
