@@ -33,6 +33,7 @@ using namespace umma;
 
 constexpr int Q = 128, HD = 64, NS = 128;
 constexpr int kThreads = 512;
+constexpr int kTmaThread = 480;  // lane 0 of warp 15 issues every TMA load / store (thread 0 issues the MMAs)
 
 constexpr uint32_t SM_X = 0;         // [head 2][Q rows x 128 B]  x bf16 -> fp16 -> X' = es dt x        32 KB
 constexpr uint32_t SM_DY = 32768;    // [head 2][Q rows x 128 B]  dy bf16 -> fp16 -> exp(Lambda_i) dy   32 KB
@@ -55,11 +56,13 @@ struct BTab {
   float cdx[2][Q];    // x_j . wd_j
   float rr[2][Q];     // <C_i, (M_0 B)_i> and <C_i, ((M_0 + M_1) B)_i>: the within-chunk part of r_i
   float roff[2][Q];   // dy_i . (exp(lam_i) C_i S_c): the incoming-state part of r_i
+  float rbase[1][Q];  // <C_i, acc_i> of what the dC accumulator held before this item (earlier head pairs of the group)
   float gii[2][Q];    // dy_i . x_i
   float zc[2];        // <dS_{c+1}, S_c>
   float lam_last[2];
   int bsafe[2][4];    // per 32-token block: decays by < 2^100, so the factorised diagonal block cannot overflow
   float wsum[2][4];   // scan scratch
+  float wsum2[2][4];
 };
 static_assert(sizeof(BTab) % 16 == 0, "BTab alignment");
 constexpr uint32_t SM_BAR = SM_TAB + sizeof(BTab);
@@ -102,6 +105,11 @@ __device__ __forceinline__ float2 bf2f2(uint32_t v) {
 __device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) {
   return pack_f16_sat(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -114,14 +122,23 @@ __device__ __forceinline__ float softplus_fast(float v) {
 
 // One 32 x 32 block of a decay-weighted matrix: out[c] = val[c] * colf[c] * rowf, optionally masked, packed to fp16.
 //   mask: 0 none, 1 keep column <= lane (lower triangle, rows i / columns j), 2 keep column >= lane (rows j / columns i)
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {  // FMUL2: two fp32 multiplies per issue slot
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rc, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
 __device__ __forceinline__ void scale_block(const uint32_t (&val)[32], const float* colf, float rowf, int mask, int lane,
                                             uint32_t (&pk)[16]) {
   const float4* cf = reinterpret_cast<const float4*>(colf);
+  const float2 rr = make_float2(rowf, rowf);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const float4 f = cf[e];
-    float p0 = __uint_as_float(val[4 * e + 0]) * rowf * f.x, p1 = __uint_as_float(val[4 * e + 1]) * rowf * f.y;
-    float p2 = __uint_as_float(val[4 * e + 2]) * rowf * f.z, p3 = __uint_as_float(val[4 * e + 3]) * rowf * f.w;
+    const float2 a01 = mul2(mul2(make_float2(__uint_as_float(val[4 * e + 0]), __uint_as_float(val[4 * e + 1])), rr), make_float2(f.x, f.y));
+    const float2 a23 = mul2(mul2(make_float2(__uint_as_float(val[4 * e + 2]), __uint_as_float(val[4 * e + 3])), rr), make_float2(f.z, f.w));
+    float p0 = a01.x, p1 = a01.y, p2 = a23.x, p3 = a23.y;
     if (mask == 1) {
       p0 = 4 * e + 0 <= lane ? p0 : 0.f; p1 = 4 * e + 1 <= lane ? p1 : 0.f;
       p2 = 4 * e + 2 <= lane ? p2 : 0.f; p3 = 4 * e + 3 <= lane ? p3 : 0.f;
@@ -195,16 +212,30 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #define dDSm make_sdesc(smem_u32(smem + SM_DS), 16384, 1024)
   auto koff = [](uint32_t k) { return ((k >> 2) << 10) + ((k & 3) << 1); };  // k-major 128-wide K: 16-byte units
 
+  // Work split: every CTA takes a CONTIGUOUS range of items, ordered (batch, chunk, head pair): consecutive items then
+  // belong to the same (batch, chunk) group, whose dC / dB (sums over the heads of the group) stay in the TMEM accumulators
+  // R2 / R3 across items and reach HBM once per group (vector reductions only because a group can straddle two CTAs).
+  const int item_lo = (int)(((int64_t)nitems * blockIdx.x) / gridDim.x), item_hi = (int)(((int64_t)nitems * (blockIdx.x + 1)) / gridDim.x);
   uint32_t ph = 0;  // mbarrier phase parity: every barrier completes exactly once per item
   int it_count = 0;
+  bool fresh = true;  // R2 / R3 hold nothing yet for the current group
+  // raw dt of (head tid >> 7, token tid & 127) of an item, for the table threads; loaded one item ahead
+  auto load_dt = [&](int item_) -> float {
+    if (tid >= 256 || item_ >= item_hi) return 0.f;
+    const int hp_ = item_ % HP, bc_ = item_ / HP, c_ = bc_ % a.nchunks, b_ = bc_ / a.nchunks;
+    const int t_ = c_ * Q + (tid & 127), h_ = hp_ * 2 + ((tid >> 7) & 1);
+    return t_ < a.L ? ld_any(a.dt, a.dt_dtype, b_ * a.dt_b + (int64_t)t_ * a.dt_l + (int64_t)h_ * a.dt_h) : 0.f;
+  };
+  float dt_next = load_dt(item_lo);
 #pragma unroll 1
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x, ph ^= 1, ++it_count) {
+  for (int item = item_lo; item < item_hi; ++item, ph ^= 1, ++it_count) {
     const int hp = item % HP, bc = item / HP, c = bc % a.nchunks, b = bc / a.nchunks;
     const int h0 = hp * 2, grp = h0 / hpg, t0 = c * Q;
+    const bool last_of_group = item + 1 == item_hi || (item + 1) / HP != bc || (h0 + 2) / hpg != grp;
 
     BTR(0);
     // ---- A. tile loads (one thread) and the decay tables (threads 0..255: head tid >> 7, token tid & 127) -----------
-    if (tid == 0) {
+    if (tid == kTmaThread) {
       mbar_expect_tx(&bars[BB_TMA], 6 * 32768);
       tma_load_4d(smem + SM_X, &mapX, &bars[BB_TMA], 0, h0, t0, b);
       tma_load_4d(smem + SM_X + 16384, &mapX, &bars[BB_TMA], 0, h0 + 1, t0, b);
@@ -225,7 +256,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const int t = t0 + tj, h = h0 + th;
       float vpre = 0.f;
       if (t < a.L) {
-        vpre = ld_any(a.dt, a.dt_dtype, b * a.dt_b + (int64_t)t * a.dt_l + (int64_t)h * a.dt_h);
+        vpre = dt_next;
         if (a.dt_bias) vpre += ld_any(a.dt_bias, a.dtb_dtype, h);
         float v = a.dt_softplus ? softplus_fast(vpre) : vpre;
         my_dt = fminf(fmaxf(v, a.dt_min), a.dt_max);
@@ -243,10 +274,15 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       tab->cdx[th][tj] = 0.f;
       tab->rr[th][tj] = 0.f;
       tab->roff[th][tj] = 0.f;
+      tab->rbase[th & 0][tj] = 0.f;
       if (tj < 2 && th == 0) tab->zc[tj] = 0.f;
     }
+    if (tid < 256) {  // (the upper half of the CTA needs lam and dt of its token too)
+      tab->lam[th][tj] = my_lam;   // still relative to the start of the token's 32-block
+      tab->dtv[th][tj] = my_dt;
+    }
     __syncthreads();
-    if (tid < 256) {
+    {
       const int wj = tj >> 5;  // 32-token block of this token
       float ref[4];            // lam just before block 0..3 (= running sum of the earlier warps' totals)
       ref[0] = 0.f;
@@ -255,59 +291,74 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       ref[3] = ref[2] + tab->wsum[th][2];
       const float lam_last = ref[3] + tab->wsum[th][3];
       const float myref = wj == 0 ? ref[0] : (wj == 1 ? ref[1] : (wj == 2 ? ref[2] : ref[3]));
-      my_lam += myref;
-      tab->lam[th][tj] = my_lam;
-      tab->dtv[th][tj] = my_dt;
-      tab->ci[th][tj] = ex2f(my_lam - myref);
-      tab->vd[th][tj] = ex2f(myref - my_lam) * my_dt;
-      tab->eL[th][tj] = ex2f(my_lam);
-      tab->es[th][tj] = ex2f(lam_last - my_lam);
+      const float rel = tid < 256 ? my_lam : tab->lam[th][tj];   // lam_j - ref(block of j)
+      const float dtj = tid < 256 ? my_dt : tab->dtv[th][tj];
+      const float lamj = rel + myref;
+      if (tid < 256) {  // lower half: the tables indexed by the token itself
+        tab->ci[th][tj] = ex2f(rel);
+        tab->vd[th][tj] = ex2f(-rel) * dtj;
+        tab->eL[th][tj] = ex2f(lamj);
+        const bool ok = __all_sync(0xffffffffu, -rel < 100.f);
+        if (lane == 0) tab->bsafe[th][wj] = ok ? 1 : 0;
+        if (tj == 0) tab->lam_last[th] = lam_last;
+      } else {          // upper half: the tables that refer to later blocks / the end of the chunk
+        tab->es[th][tj] = ex2f(lam_last - lamj);
 #pragma unroll
-      for (int w = 1; w < 4; ++w)
-        if (wj < w) tab->v[th][w - 1][tj] = ex2f(ref[w] - my_lam) * my_dt;
-      const bool ok = __all_sync(0xffffffffu, myref - my_lam < 100.f);
-      if (lane == 0) tab->bsafe[th][wj] = ok ? 1 : 0;
-      if (tj == 0) tab->lam_last[th] = lam_last;
+        for (int w = 1; w < 4; ++w)
+          if (wj < w) tab->v[th][w - 1][tj] = ex2f(ref[w] - lamj) * dtj;
+      }
+      __syncthreads();  // every thread has read the block-relative lam before it is replaced by the chunk-wide value
+      if (tid < 256) tab->lam[th][tj] = lamj;
     }
-
-    // ---- B. x, dy: bf16 -> fp16 in place --------------------------------------------------------------------------------
     BTR(1);
     mbar_wait(&bars[BB_TMA], ph);
     BTR(2);
-    {
-      uint4* xt = reinterpret_cast<uint4*>(smem + SM_X);  // SM_X and SM_DY are adjacent: 4096 16-byte slots
-#pragma unroll 1
-      for (int k = 0; k < 8; ++k) {
-        const int slot = tid + 512 * k;
-        uint4 v = xt[slot];
-        v.x = bf16x2_to_f16x2(v.x); v.y = bf16x2_to_f16x2(v.y); v.z = bf16x2_to_f16x2(v.z); v.w = bf16x2_to_f16x2(v.w);
-        xt[slot] = v;
-      }
+    if (tid == kTmaThread && item + 1 < item_hi) {  // next item's x / dy / S / dS tiles -> L2 while this item computes
+      const int hp1 = (item + 1) % HP, bc1 = (item + 1) / HP, c1 = bc1 % a.nchunks, b1 = bc1 / a.nchunks, g1 = hp1 * 2;
+      tma_prefetch_4d(&mapX, 0, g1, c1 * Q, b1);
+      tma_prefetch_4d(&mapX, 0, g1 + 1, c1 * Q, b1);
+      tma_prefetch_4d(&mapDY, 0, g1, c1 * Q, b1);
+      tma_prefetch_4d(&mapDY, 0, g1 + 1, c1 * Q, b1);
+      tma_prefetch_4d(&mapS, 0, g1 * HD, c1, b1);
+      tma_prefetch_4d(&mapS, 64, g1 * HD, c1, b1);
+      tma_prefetch_4d(&mapDS, 0, g1 * HD, c1, b1);
+      tma_prefetch_4d(&mapDS, 64, g1 * HD, c1, b1);
     }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-
-    BTR(3);
-    // ---- C. G1: CB^T = B C^T -> R0;  G3: ws = B dS16^T -> R1 -----------------------------------------------------------
+    // ---- C. G1: CB^T = B C^T -> R0;  G3: ws = B dS16^T -> R1  (neither needs x / dy: issued before their conversion) ----
     if (tid == 0) {
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R0, dBk + koff(k), dCk + koff(k), id_kk, k > 0);
-#pragma unroll 1
+#pragma unroll
       for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R1, dBk + koff(k), dDSk + koff(k), id_kk, k > 0);
       mma_commit(&bars[BB_C1]);
     }
+    // ---- B. x, dy: bf16 -> fp16 in place (while G1 / G3 run) --------------------------------------------------------------
+    {
+      uint4* xt = reinterpret_cast<uint4*>(smem + SM_X);  // SM_X and SM_DY are adjacent: 4096 16-byte slots
+#pragma unroll 2
+      for (int k = 0; k < 8; ++k) {
+        uint4 v = xt[tid + 512 * k];
+        v.x = bf16x2_to_f16x2(v.x); v.y = bf16x2_to_f16x2(v.y); v.z = bf16x2_to_f16x2(v.z); v.w = bf16x2_to_f16x2(v.w);
+        xt[tid + 512 * k] = v;
+      }
+    }
+    fence_proxy_async_smem();
+    BTR(3);
     // ---- D. PT_h[j][i] = CB^T[j][i] L_ij (i >= j), fp16, in place (rows j, 32-column block ib = wq) ---------------------
-    mbar_wait(&bars[BB_C1], ph);   // (the __syncthreads of phase B also published the tables)
+    __syncthreads();               // tables (and the fp16 tiles) published
+    mbar_wait(&bars[BB_C1], ph);
     BTR(4);
     bool safe = true;
 #pragma unroll
     for (int e = 0; e < 8; ++e) safe = safe && (&tab->bsafe[0][0])[e] != 0;
     tc_fence_after();
+    uint32_t wsr[2][16];  // ws of this thread's (row j, 16 columns p = 16 wq ..) for both heads: R1 is re-used for wd
     {
       uint32_t cbt[32];
       tmem_ld32(tmem_addr(tb, q * 32, R0 + 32 * wq), cbt);  // (unconditional: a predicated load would put cbt in local memory)
+      tmem_ld16(tmem_addr(tb, q * 32, R1 + 16 * wq), wsr[0]);
+      tmem_ld16(tmem_addr(tb, q * 32, R1 + 64 + 16 * wq), wsr[1]);
       tmem_ld_wait();
       tc_fence_before();
       __syncthreads();  // every block is in registers before any warp overwrites the region with fp16
@@ -331,63 +382,16 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     tc_fence_before();
     __syncthreads();
     BTR(5);
-    // ---- E. G2: wd_h = PT_h dy_h -> R2 + 64 h ----------------------------------------------------------------------
+    // ---- E. G2: wd_h = PT_h dy_h -> R1 + 64 h ----------------------------------------------------------------------
     if (tid == 0) {
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (uint32_t hk = 0; hk < 16; ++hk) {
         const uint32_t h = hk >> 3, k = hk & 7;
-        mma_ts(tb + R2 + 64 * h, tb + R0 + 64 * h + 8 * k, dDYm + h * 1024 + k * 128, id_ts64, k > 0);
+        mma_ts(tb + R1 + 64 * h, tb + R0 + 64 * h + 8 * k, dDYm + h * 1024 + k * 128, id_ts64, k > 0);
       }
       mma_commit(&bars[BB_C2]);
     }
-    // ---- F. dx_j = dt_j (wd_j + es_j ws_j) + D dy_j; x.w and x.wd row sums; one head at a time through the staging tile --
-    mbar_wait(&bars[BB_C2], ph);
-    BTR(6);
-    tc_fence_after();
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      uint32_t wd[16], ws[16];
-      tmem_ld16(tmem_addr(tb, q * 32, R2 + 64 * h + 16 * wq), wd);
-      tmem_ld16(tmem_addr(tb, q * 32, R1 + 64 * h + 16 * wq), ws);
-      tmem_ld_wait();
-      const float esj = tab->es[h][row], dtj = tab->dtv[h][row];
-      const float Dh = a.D ? ld_any(a.D, a.D_dtype, h0 + h) : 0.f;
-      float sw = 0.f, swd = 0.f;
-      if (h == 1) {  // the staging tile is reused: the TMA store of head 0 must have read it
-        if (tid == 0) tma_store_wait_read<0>();
-        __syncthreads();
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const uint32_t off = h * 16384 + sw128(row, 2 * wq + k);
-        const uint4 xv = *reinterpret_cast<const uint4*>(smem + SM_X + off);
-        const uint4 dv = *reinterpret_cast<const uint4*>(smem + SM_DY + off);
-        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 xf = h2f2(xw[e]), df = h2f2(dw[e]);
-          const float d0 = __uint_as_float(wd[8 * k + 2 * e]), d1 = __uint_as_float(wd[8 * k + 2 * e + 1]);
-          const float w0 = d0 + esj * __uint_as_float(ws[8 * k + 2 * e]), w1 = d1 + esj * __uint_as_float(ws[8 * k + 2 * e + 1]);
-          sw += xf.x * w0 + xf.y * w1;
-          swd += xf.x * d0 + xf.y * d1;
-          o[e] = pack_bf16(dtj * w0 + Dh * df.x, dtj * w1 + Dh * df.y);
-        }
-        *reinterpret_cast<uint4*>(smem + SM_STG + sw128(row, 2 * wq + k)) = make_uint4(o[0], o[1], o[2], o[3]);
-      }
-      atomicAdd(&tab->ddtd[h][row], sw);
-      atomicAdd(&tab->cdx[h][row], swd);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {  // rows beyond L are clipped by the tensor map
-        tma_store_4d(&mapDX, smem + SM_STG, 0, h0 + h, t0, b);
-        tma_store_commit();
-      }
-    }
-    BTR(7);
-    // ---- G. G4: G_h0 = dy_h0 x_h0^T -> R0;  G4': G_h0^T -> R1 ---------------------------------------------------------
     // <C_i, acc_i> over this warp's 32 columns n of the dC accumulator (row i = `row`), added to dst[row]
     auto dot_c_acc = [&](float* dst) {
       uint32_t v[32];
@@ -409,10 +413,58 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       }
       atomicAdd(&dst[row], part);
     };
+    if (!fresh) dot_c_acc(tab->rbase[0]);  // what the dC accumulator already holds from earlier items of the group
+    // ---- F. dx_j = dt_j (wd_j + es_j ws_j) + D dy_j; x.w and x.wd row sums; one head at a time through the staging tile --
+    mbar_wait(&bars[BB_C2], ph);
+    BTR(6);
+    tc_fence_after();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t wd[16];
+      tmem_ld16(tmem_addr(tb, q * 32, R1 + 64 * h + 16 * wq), wd);
+      tmem_ld_wait();
+      const float esj = tab->es[h][row], dtj = tab->dtv[h][row];
+      const float Dh = a.D ? ld_any(a.D, a.D_dtype, h0 + h) : 0.f;
+      float sw = 0.f, swd = 0.f;
+      if (h == 1) {  // the staging tile is reused: the TMA store of head 0 must have read it
+        if (tid == kTmaThread) tma_store_wait_read<0>();
+        __syncthreads();
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const uint32_t off = h * 16384 + sw128(row, 2 * wq + k);
+        const uint4 xv = *reinterpret_cast<const uint4*>(smem + SM_X + off);
+        const uint4 dv = *reinterpret_cast<const uint4*>(smem + SM_DY + off);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 xf = h2f2(xw[e]), df = h2f2(dw[e]);
+          const float d0 = __uint_as_float(wd[8 * k + 2 * e]), d1 = __uint_as_float(wd[8 * k + 2 * e + 1]);
+          const float w0 = d0 + esj * __uint_as_float(wsr[h][8 * k + 2 * e]), w1 = d1 + esj * __uint_as_float(wsr[h][8 * k + 2 * e + 1]);
+          sw += xf.x * w0 + xf.y * w1;
+          swd += xf.x * d0 + xf.y * d1;
+          o[e] = pack_bf16(dtj * w0 + Dh * df.x, dtj * w1 + Dh * df.y);
+        }
+        *reinterpret_cast<uint4*>(smem + SM_STG + sw128(row, 2 * wq + k)) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      atomicAdd(&tab->ddtd[h][row], sw);
+      atomicAdd(&tab->cdx[h][row], swd);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == kTmaThread) {  // rows beyond L are clipped by the tensor map
+        tma_store_4d(&mapDX, smem + SM_STG, 0, h0 + h, t0, b);
+        tma_store_commit();
+      }
+    }
+    BTR(7);
+    dt_next = load_dt(item + 1);  // in flight during the rest of this item
+    // ---- G. G4: G_h0 = dy_h0 x_h0^T -> R0;  G4': G_h0^T -> R1 ---------------------------------------------------------
     auto issue_g = [&](uint32_t h) {
-#pragma unroll 1
+#pragma unroll
       for (uint32_t k = 0; k < 4; ++k) mma_ss(tb + R0, dDYk + h * 1024 + 2 * k, dXk + h * 1024 + 2 * k, id_kk, k > 0);
-#pragma unroll 1
+#pragma unroll
       for (uint32_t k = 0; k < 4; ++k) mma_ss(tb + R1, dXk + h * 1024 + 2 * k, dDYk + h * 1024 + 2 * k, id_kk, k > 0);
     };
     if (tid == 0) {
@@ -426,7 +478,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       mbar_wait(&bars[h == 0 ? BB_C3 : BB_C4], ph);
       BTR(8 + 2 * h);
       tc_fence_after();
-      if (h == 1) dot_c_acc(tab->rr[0]);  // the dC accumulator holds M_0 B only: head 0's within-chunk part of r_i
+      if (h == 1) dot_c_acc(tab->rr[0]);  // base + M_0 B: head 0's within-chunk part of r_i
       uint32_t pk[16];
       {  // M block (row i = `row`, column block jb = wq): the source block is in registers before any warp stores fp16
         uint32_t g[32];
@@ -475,10 +527,11 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       // ---- I/K. G5: dC (+)= M_h B -> R2;  G7: dB (+)= MT_h C -> R3;  then the next head's G / G^T ----------------------
       if (tid == 0) {
         tc_fence_after();
-#pragma unroll 1
-        for (uint32_t k = 0; k < 8; ++k) mma_ts(tb + R2, tb + R0 + 8 * k, dBm + k * 128, id_ts128, (h | k) != 0);
-#pragma unroll 1
-        for (uint32_t k = 0; k < 8; ++k) mma_ts(tb + R3, tb + R1 + 8 * k, dCm + k * 128, id_ts128, (h | k) != 0);
+        const bool first = fresh && h == 0;  // the accumulators start a new (batch, chunk) group
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) mma_ts(tb + R2, tb + R0 + 8 * k, dBm + k * 128, id_ts128, !(first && k == 0));
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) mma_ts(tb + R3, tb + R1 + 8 * k, dCm + k * 128, id_ts128, !(first && k == 0));
         if (h == 0) {
           issue_g(1);
           mma_commit(&bars[BB_C4]);
@@ -487,61 +540,45 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
       }
     }
-    // ---- L. x16 -> X' = es dt x, dy16 -> exp(lam_i) dy, in place;  zc_h = <dS_{c+1}, S_c> ---------------------------------
+    // ---- L. x16 -> X' = es dt x, dy16 -> exp(lam_i) dy, in place (packed fp16 multiplies) ----------------------------------
     mbar_wait(&bars[BB_C5], ph);
     BTR(12);
     tc_fence_after();
-    dot_c_acc(tab->rr[1]);  // (M_0 + M_1) B: both heads' within-chunk parts
+    dot_c_acc(tab->rr[1]);  // base + (M_0 + M_1) B: both heads' within-chunk parts
     {
       uint4* xt = reinterpret_cast<uint4*>(smem + SM_X);
-#pragma unroll 1
+#pragma unroll 2
       for (int k = 0; k < 8; ++k) {
         const int slot = tid + 512 * k;
         const int r = (slot >> 3) & 127, hh = (slot >> 10) & 1;
         const float s = slot < 2048 ? tab->es[hh][r] * tab->dtv[hh][r] : tab->eL[hh][r];
+        const __half2 s2 = __float2half2_rn(s);
         uint4 v = xt[slot];
-        const float2 f0 = h2f2(v.x), f1 = h2f2(v.y), f2 = h2f2(v.z), f3 = h2f2(v.w);
-        v.x = pack_f16_sat(f0.x * s, f0.y * s); v.y = pack_f16_sat(f1.x * s, f1.y * s);
-        v.z = pack_f16_sat(f2.x * s, f2.y * s); v.w = pack_f16_sat(f3.x * s, f3.y * s);
+        __half2* hv = reinterpret_cast<__half2*>(&v);
+        hv[0] = __hmul2(hv[0], s2); hv[1] = __hmul2(hv[1], s2); hv[2] = __hmul2(hv[2], s2); hv[3] = __hmul2(hv[3], s2);
         xt[slot] = v;
-      }
-      const uint4* st = reinterpret_cast<const uint4*>(smem + SM_S);
-      const uint4* dst = reinterpret_cast<const uint4*>(smem + SM_DS);
-      float z[2] = {0.f, 0.f};  // slot tid + 512 k: row (slot >> 3) & 127, head = row >> 6 = bit 9 of the slot = k & 1
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint4 sv = st[tid + 512 * k], dv = dst[tid + 512 * k];
-        const uint32_t sw_[4] = {sv.x, sv.y, sv.z, sv.w}, dw_[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 sf = h2f2(sw_[e]), df = h2f2(dw_[e]);
-          z[k & 1] += sf.x * df.x + sf.y * df.y;
-        }
-      }
-      z[0] = warp_sum(z[0]);
-      z[1] = warp_sum(z[1]);
-      if (lane == 0) {
-        atomicAdd(&tab->zc[0], z[0]);
-        atomicAdd(&tab->zc[1], z[1]);
       }
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     BTR(13);
-    // ---- M. G6: dC += (exp(lam) dy) S_c -> R2;  G8: dB += X' dS_{c+1} -> R3 ------------------------------------------------
+    // ---- M. G6: dC += (exp(lam) dy) S_c -> R2;  G8: dB += X' dS_{c+1} -> R3;  G10: C S16^T -> R0;  G11: dS16 S16^T -> R1 ----
     if (tid == 0) {
       tc_fence_after();
       const uint32_t id_kmn = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorMN);
-#pragma unroll 1
+#pragma unroll
       for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R2, dDYk + koff(k), dSm + k * 128, id_kmn, true);
-#pragma unroll 1
+#pragma unroll
       for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R3, dXk + koff(k), dDSm + k * 128, id_kmn, true);
-#pragma unroll 1
-      for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R0, dCk + koff(k), dSk + koff(k), id_kk, k > 0);  // G10: C S16^T
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R0, dCk + koff(k), dSk + koff(k), id_kk, k > 0);    // G10
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R1, dDSk + koff(k), dSk + koff(k), id_kk, k > 0);   // G11
       mma_commit(&bars[BB_C6]);
     }
-    // ---- N0. roff_i = (exp(lam_i) dy_i) . (C_i S_c): rows i, this warp's 32 columns (h, p) of G10 --------------------------
+    // ---- N0. roff_i = (exp(lam_i) dy_i) . (C_i S_c): rows i, this warp's 32 columns (h, p) of G10;
+    //          zc_h = <dS_{c+1}, S_c> = the trace of G11 over the head's 64 rows ------------------------------------------
     mbar_wait(&bars[BB_C6], ph);
     BTR(14);
     tc_fence_after();
@@ -564,69 +601,77 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
       }
       atomicAdd(&tab->roff[wq >> 1][row], part);
+      if (wq == 0) {  // diagonal element (row, row) of G11: the lane-th of this warp's 32 diagonal-block columns
+        uint32_t dg[32];
+        tmem_ld32(tmem_addr(tb, q * 32, R1 + 32 * q), dg);
+        tmem_ld_wait();
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) d = e == lane ? __uint_as_float(dg[e]) : d;
+        const float zs = warp_sum(d);
+        if (lane == 0) atomicAdd(&tab->zc[q >> 1], zs);
+      }
     }
     tc_fence_before();
     __syncthreads();
-    // ---- N1. da, ddt and the per-(batch, head) parameter sums (warps 0, 1: one head each) --------------------------------
-    if (warp < 2) {
-      const int h = warp, hg = h0 + h;
-      const float Ah = a.A[hg];
-      const float dch = ex2f(tab->lam_last[h]);
-      // per lane: tokens 4 lane .. 4 lane + 3
-      float e1[4], e2[4], dtk[4];
-      float s1 = 0.f, s2 = 0.f, sD = 0.f;
+    // ---- N1. da, ddt and the per-(batch, head) parameter sums: warps 0-3 head 0, warps 4-7 head 1, one token per lane ----
+    {
+      const int h = (warp >> 2) & 1, hg = h0 + h, j = (warp & 3) * 32 + lane;
+      float e1 = 0.f, e2 = 0.f, dtk = 0.f, i1 = 0.f, i2 = 0.f;
+      if (warp < 8) {
+        dtk = tab->dtv[h][j];
+        const float cd = dtk * tab->cdx[h][j];                       // x_j . dxdiag_j
+        e2 = dtk * (tab->ddtd[h][j] - tab->cdx[h][j]);               // x_j . dxstate_j
+        const float r = (h == 0 ? tab->rr[0][j] - tab->rbase[0][j] : tab->rr[1][j] - tab->rr[0][j]) + tab->roff[h][j];  // dy_j . (y_j - D x_j)
+        e1 = r - cd;
+        i1 = e1; i2 = e2;  // inclusive warp scans
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int j = 4 * lane + k;
-        dtk[k] = tab->dtv[h][j];
-        const float cd = dtk[k] * tab->cdx[h][j];                        // x_j . dxdiag_j
-        const float cs = dtk[k] * (tab->ddtd[h][j] - tab->cdx[h][j]);   // x_j . dxstate_j
-        const float r = (h == 0 ? tab->rr[0][j] : tab->rr[1][j] - tab->rr[0][j]) + tab->roff[h][j];  // dy_j . (y_j - D x_j)
-        e1[k] = r - cd;
-        e2[k] = cs;
-        s1 += e1[k]; s2 += e2[k]; sD += tab->gii[h][j];
+        for (int o = 1; o < 32; o <<= 1) {
+          const float u1 = __shfl_up_sync(0xffffffffu, i1, o), u2 = __shfl_up_sync(0xffffffffu, i2, o);
+          if (lane >= o) { i1 += u1; i2 += u2; }
+        }
+        if (lane == 31) { tab->wsum[h][warp & 3] = i1; tab->wsum2[h][warp & 3] = i2; }
       }
-      float i1 = s1, i2 = s2;  // inclusive warp scans of the per-lane totals
+      __syncthreads();
+      if (warp < 8) {
+        const int wj = warp & 3;
+        float before1 = 0.f, before2 = 0.f, tot1 = 0.f;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float u1 = __shfl_up_sync(0xffffffffu, i1, o), u2 = __shfl_up_sync(0xffffffffu, i2, o);
-        if (lane >= o) { i1 += u1; i2 += u2; }
-      }
-      const float tot1 = __shfl_sync(0xffffffffu, i1, 31);
-      float rev = tot1 - (i1 - s1);   // sum of e1 over tokens >= 4 lane
-      float fwd = i2 - s2;            // sum of e2 over tokens < 4 lane
-      const float zc = dch * tab->zc[h];
-      float sA = 0.f, sB = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int j = 4 * lane + k, t = t0 + j;
-        const float da = rev + fwd + zc;   // revcumsum_incl(e1)_j + cumsum_excl(e2)_j + <dS, d S>
-        rev -= e1[k];
-        fwd += e2[k];
-        float ddt = tab->ddtd[h][j] + Ah * da;
-        sA += dtk[k] * da;
+        for (int w = 0; w < 4; ++w) {
+          const float t1 = tab->wsum[h][w], t2 = tab->wsum2[h][w];
+          tot1 += t1;
+          if (w < wj) { before1 += t1; before2 += t2; }
+        }
+        const float rev = tot1 - (before1 + i1 - e1);   // sum of e1 over tokens >= j
+        const float fwd = before2 + i2 - e2;            // sum of e2 over tokens < j
+        const float da = rev + fwd + ex2f(tab->lam_last[h]) * tab->zc[h];
+        float ddt = tab->ddtd[h][j] + a.A[hg] * da;
+        float sA = dtk * da, sB = 0.f, sD = tab->gii[h][j];
         // back through clamp and softplus
         const float vpre = tab->vpre[h][j];
         const float vact = a.dt_softplus ? softplus_fast(vpre) : vpre;
         if (vact < a.dt_min || vact > a.dt_max) ddt = 0.f;
         if (a.dt_softplus && vpre <= 20.f) ddt *= 1.f / (1.f + __expf(-vpre));
+        const int t = t0 + j;
         if (t < a.L) {
           st_any(a.ddt, a.ddt_dtype, b * a.ddt_b + (int64_t)t * a.ddt_l + (int64_t)hg * a.ddt_h, ddt);
-          sB += ddt;
+          sB = ddt;
+        }
+        sA = warp_sum(sA); sB = warp_sum(sB); sD = warp_sum(sD);
+        if (lane == 0) {
+          atomicAdd(a.dA_part + b * a.H + hg, sA);
+          atomicAdd(a.ddtb_part + b * a.H + hg, sB);
+          atomicAdd(a.dD_part + b * a.H + hg, sD);
         }
       }
-      sA = warp_sum(sA); sB = warp_sum(sB); sD = warp_sum(sD);
-      if (lane == 0) {
-        atomicAdd(a.dA_part + b * a.H + hg, sA);
-        atomicAdd(a.ddtb_part + b * a.H + hg, sB);
-        atomicAdd(a.dD_part + b * a.H + hg, sD);
-      }
     }
-    // ---- N2. dC (R2), dB (R3): TMEM -> fp32 staging over the dead x/dy and B/C tiles -> coalesced vector reductions ----
     BTR(15);
-    __syncthreads();  // (warps 0, 1 still read the C / dy tiles through the tables only: the tiles themselves are dead)
-    BTR(16);
-    {
+    fresh = false;
+    // ---- N2. end of a (batch, chunk) group: dC (R2), dB (R3): TMEM -> fp32 staging over the dead x/dy and B/C tiles ->
+    //          coalesced vector reductions ----------------------------------------------------------------------------------
+    if (last_of_group) {
+      __syncthreads();
+      BTR(16);
       float* stC = reinterpret_cast<float*>(smem + SM_X);   // [128 rows][32 float4 chunks], chunk slot = chunk ^ (row & 31)
       float* stB = reinterpret_cast<float*>(smem + SM_B);
 #pragma unroll 1
@@ -651,13 +696,14 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           red_add_v4(gp, val.x, val.y, val.z, val.w);
         }
       }
+      fresh = true;
     }
     BTR(17);
-    if (tid == 0) tma_store_wait_read<0>();  // the dx staging tile and the next item's loads
+    if (tid == kTmaThread) tma_store_wait_read<0>();  // the dx staging tile and the next item's loads
     tc_fence_before();
     __syncthreads();
   }
-  if (tid == 0) tma_store_wait_all<0>();
+  if (tid == kTmaThread) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tb, 512);
