@@ -46,7 +46,7 @@ using namespace umma;
 constexpr int Q = 128;     // tokens per chunk
 constexpr int HD = 64;     // headdim
 constexpr int NS = 128;    // d_state
-constexpr int kThreads = 512;
+constexpr int kThreads = 512;   // 16 warps: 2 table, TMA, MMA, 8 P build + x pass, 4 epilogue + state
 
 // shared-memory map (bytes, relative to the 1024B-aligned base)
 constexpr uint32_t SM_XA = 0;           // [head 2][Q rows x 128 B]  x bf16 (TMA) -> fp16 in place            32 KB
@@ -71,7 +71,10 @@ static_assert(sizeof(Tab) % 16 == 0, "Tab alignment");
 constexpr uint32_t SM_BAR = SM_TAB + 2 * sizeof(Tab);
 enum {
   B_FULL_B = 0, B_EMPTY_B = 2, B_TAB_READY = 4, B_TAB_FREE = 6,
-  B_FULL_C = 8, B_FULL_X, B_CB_DONE, B_P_READY, B_X16_READY, B_S_READY, B_YOFF_DONE, B_U_DONE, B_YD_DONE, B_ACC_FREE, B_COUNT
+  B_FULL_C = 8, B_FULL_X, B_CB_DONE, B_P_READY, B_X16_READY, B_S_READY, B_YOFF_DONE, B_U_DONE, B_YD_DONE,
+  B_ACC_FREE = 17,  // [head 2] epilogue has read both accumulators of the head
+  B_DX_READY = 19,  // [head 2] x pass part (b): D x is in the head's Ydiag accumulator
+  B_COUNT = 21
 };
 constexpr uint32_t SM_TMEMPTR = SM_BAR + B_COUNT * 8;
 constexpr uint32_t SM_TOTAL = SM_TMEMPTR + 16;
@@ -171,7 +174,9 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       mbar_init(&bars[B_FULL_B + i], 1);
       mbar_init(&bars[B_EMPTY_B + i], 1);
       mbar_init(&bars[B_TAB_READY + i], 2);
-      mbar_init(&bars[B_TAB_FREE + i], 12);
+      mbar_init(&bars[B_TAB_FREE + i], 12);  // 8 P / x-pass warps + 4 epilogue / state warps
+      mbar_init(&bars[B_ACC_FREE + i], 4);
+      mbar_init(&bars[B_DX_READY + i], 4);
     }
     mbar_init(&bars[B_FULL_C], 1);
     mbar_init(&bars[B_FULL_X], 1);
@@ -182,7 +187,6 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     mbar_init(&bars[B_YOFF_DONE], 1);
     mbar_init(&bars[B_U_DONE], 1);
     mbar_init(&bars[B_YD_DONE], 1);
-    mbar_init(&bars[B_ACC_FREE], 4);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -195,6 +199,19 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = *tmem_ptr;
+  // Waits.  try_wait suspends the thread, but a suspended thread is woken by every mbarrier event of the CTA (TMA byte
+  // counts included), and each wake-up costs issue slots that the working warps of the same scheduler need (a third of
+  // all executed instructions were wait loops).  Roles made of several warps therefore let ONE warp watch the mbarrier
+  // and park the others on a hardware named barrier, which costs nothing while waiting.
+  const uint32_t hint = g_mbar_hint_ns;
+  auto wait1 = [&](uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(smem_u32(&bars[bar])), "r"(parity), "r"(hint) : "memory");
+    } while (!ok);
+  };
 
   const int HP = a.H >> 1;                    // head pairs
   const int nitems = a.B * HP;
@@ -211,7 +228,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   const int mode = a.mode;
   auto cphys = [&](int c) { return mode == 2 ? nchunks - 1 - c : c; };  // chunk visited at step c of an item
 
-  if (warp == 0) {
+  if (warp == 2) {
     // ============ TMA producer ========================================================================================
     if (lane == 0 && total > 0) {
       auto load_b = [&](const ChunkIter& it, uint32_t st) {
@@ -249,24 +266,24 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       for (uint32_t g = 0; g + 1 < total; ++g) {
         if (g + 2 < total) prefetch(it2);
         if (mode == 0) {
-          mbar_wait(&bars[B_YOFF_DONE], g & 1);            // Yoff(g) has read C(g)
+          wait1(B_YOFF_DONE, g & 1);            // Yoff(g) has read C(g)
           TR(2);
           load_c(it1);
         }
+        if (mode == 0) wait1(B_YD_DONE, g & 1);   // Ydiag(g) has read x(g)
+        else wait1(B_X16_READY, g & 1);           // (state sweeps: the x pass has read it)
+        TR(0);
+        load_x(it1);
         if (g + 2 < total) {
-          mbar_wait(&bars[B_EMPTY_B + (g & 1)], (g >> 1) & 1);  // S-update(g) has read B stage g & 1
+          wait1(B_EMPTY_B + (g & 1), (g >> 1) & 1);  // S-update(g) has read B stage g & 1
           TR(1);
           load_b(it2, g & 1);
         }
-        if (mode == 0) mbar_wait(&bars[B_YD_DONE], g & 1);   // Ydiag(g) has read x(g)
-        else mbar_wait(&bars[B_X16_READY], g & 1);           // (state sweeps: the x pass has read it)
-        TR(0);
-        load_x(it1);
         it_next(it1);
         it_next(it2);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 3) {
     // ============ MMA issuer ==========================================================================================
     if (lane == 0 && total > 0) {
       const uint32_t id_nn = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
@@ -283,9 +300,9 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const uint64_t dBk = make_sdesc(smem_u32(smem + SM_B + st * 32768), 16, 1024);
         const uint64_t dBm = make_sdesc(smem_u32(smem + SM_B + st * 32768), 16384, 1024);
         if (mode != 0) {  // state sweeps: only the state update
-          mbar_wait(&bars[B_FULL_B + st], n & 1);
-          mbar_wait(&bars[B_S_READY], ph);
-          mbar_wait(&bars[B_X16_READY], ph);
+          wait1(B_FULL_B + st, n & 1);
+          wait1(B_S_READY, ph);
+          wait1(B_X16_READY, ph);
           tc_fence_after();
 #pragma unroll 1
           for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + TM_S, dXB + k * 128, dBm + k * 128, id_u, true);
@@ -293,52 +310,77 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           mma_commit(&bars[B_EMPTY_B + st]);
           continue;
         }
-        // CB = C B^T
-        mbar_wait(&bars[B_FULL_B + st], n & 1);
-        mbar_wait(&bars[B_FULL_C], ph);
-        tc_fence_after();
-        TR(3);
-#pragma unroll 1
-        for (uint32_t k = 0; k < 8; ++k) {
-          const uint32_t off = ((k >> 2) << 10) + ((k & 3) << 1);
-          mma_ss(tb + TM_CB, dC + off, dBk + off, id_nn, k > 0);
+        // Issue order per chunk: Yoff(g) | Ydiag(g) | CB(g+1) | S-update(g).  The epilogue only needs the first two, CB(g+1)
+        // must follow Ydiag(g) (P lives where CB lands) and feeds the next P build, and the state update has a whole
+        // chunk of slack (its consumers are the next chunk's state keepers and x pass).
+        if (g == 0) {
+          wait1(B_FULL_B + 0, 0);
+          wait1(B_FULL_C, 0);
+          tc_fence_after();
+          TR(3);
+#pragma unroll
+          for (uint32_t k = 0; k < 8; ++k) {
+            const uint32_t off = ((k >> 2) << 10) + ((k & 3) << 1);
+            mma_ss(tb + TM_CB, dC + off, dBk + off, id_nn, k > 0);
+          }
+          mma_commit(&bars[B_CB_DONE]);
         }
-        mma_commit(&bars[B_CB_DONE]);
-        // Yoff = C S16^T  (state entering the chunk)
-        mbar_wait(&bars[B_S_READY], ph);
-        if (g > 0) mbar_wait(&bars[B_ACC_FREE], ph ^ 1);
+        // Yoff = C S16^T  (state entering the chunk); first, so that C(g) is released early (its reload must land before
+        // CB(g+1)) - it only needs the state copy and the accumulators the previous epilogue has read
+        wait1(B_S_READY, ph);
+        if (g > 0) {
+          wait1(B_ACC_FREE + 0, ph ^ 1);
+          wait1(B_ACC_FREE + 1, ph ^ 1);
+        }
         tc_fence_after();
         TR(4);
-#pragma unroll 1
+#pragma unroll
         for (uint32_t k = 0; k < 8; ++k) {
           const uint32_t off = ((k >> 2) << 10) + ((k & 3) << 1);
           mma_ss(tb + TM_YOFF, dC + off, dS + off, id_nn, k > 0);
         }
         mma_commit(&bars[B_YOFF_DONE]);
-        // S += X'^T B   (S was rescaled by exp(lam_last) by the state keepers)
-        mbar_wait(&bars[B_X16_READY], ph);
+        // Ydiag_h (+)= P_h x_h   (the accumulator already holds D x)
+        wait1(B_P_READY, ph);
+#pragma unroll
+        for (uint32_t h = 0; h < 2; ++h) {
+          wait1(B_DX_READY + h, ph);
+          tc_fence_after();
+          if (h == 0) TR(6);
+#pragma unroll
+          for (uint32_t k = 0; k < 8; ++k)
+            mma_ts(tb + TM_YD + 64 * h, tb + TM_CB + 32 * (k >> 1) + 16 * h + 8 * (k & 1), dXA + h * 1024 + k * 128, id_yd,
+                   (has_D | k) != 0);
+        }
+        mma_commit(&bars[B_YD_DONE]);
+        // CB(g+1) = C B^T of the next chunk
+        if (g + 1 < total) {
+          const uint32_t st1 = (g + 1) & 1;
+          const uint64_t dBk1 = make_sdesc(smem_u32(smem + SM_B + st1 * 32768), 16, 1024);
+          wait1(B_FULL_B + st1, ((g + 1) >> 1) & 1);
+          wait1(B_FULL_C, ph ^ 1);
+          tc_fence_after();
+          TR(3);
+#pragma unroll
+          for (uint32_t k = 0; k < 8; ++k) {
+            const uint32_t off = ((k >> 2) << 10) + ((k & 3) << 1);
+            mma_ss(tb + TM_CB, dC + off, dBk1 + off, id_nn, k > 0);
+          }
+          mma_commit(&bars[B_CB_DONE]);
+        }
+        // S += X'^T B   (S was rescaled by exp(lam_last) by the state keepers; X16_READY: part (a) of the x pass)
+        wait1(B_X16_READY, ph);
         tc_fence_after();
         TR(5);
-#pragma unroll 1
+#pragma unroll
         for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + TM_S, dXB + k * 128, dBm + k * 128, id_u, true);
         mma_commit(&bars[B_U_DONE]);
         mma_commit(&bars[B_EMPTY_B + st]);
-        // Ydiag_h (+)= P_h x_h   (the accumulator already holds D x when D is given)
-        mbar_wait(&bars[B_P_READY], ph);
-        tc_fence_after();
-        TR(6);
-#pragma unroll 1
-        for (uint32_t hk = 0; hk < 16; ++hk) {
-          const uint32_t h = hk >> 3, k = hk & 7;
-          mma_ts(tb + TM_YD + 64 * h, tb + TM_CB + 32 * (k >> 1) + 16 * h + 8 * (k & 1), dXA + h * 1024 + k * 128, id_yd,
-                 (has_D | k) != 0);
-        }
-        mma_commit(&bars[B_YD_DONE]);
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < 2) {
     // ============ table warps (one head each): dt transform, decay cumsum, exp tables ================================
-    const int hh = warp - 2;
+    const int hh = warp;
     uint32_t raw[4];  // raw dt bits of the NEXT chunk: loaded a chunk ahead, converted only when used
     auto load_raw = [&](const ChunkIter& it, bool valid) {
       const int64_t base = it.b * a.dt_b + (int64_t)(it.h0 + hh) * a.dt_h;
@@ -399,37 +441,38 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       float ref[3];
 #pragma unroll
       for (int w = 1; w < 4; ++w) ref[w - 1] = __shfl_sync(0xffffffffu, lam[3], 8 * w - 1);
-      mbar_wait(&bars[B_TAB_FREE + st], (n & 1) ^ 1);
+      // every table entry is computed before waiting for the slot, so that only the stores sit behind the wait
+      float4 l4 = make_float4(lam[0], lam[1], lam[2], lam[3]), d4 = make_float4(dtv[0], dtv[1], dtv[2], dtv[3]), s4, e4, vd4;
+      float4 v4[3];
+      s4.x = ex2f(lam_last - lam[0]) * dtv[0]; s4.y = ex2f(lam_last - lam[1]) * dtv[1];
+      s4.z = ex2f(lam_last - lam[2]) * dtv[2]; s4.w = ex2f(lam_last - lam[3]) * dtv[3];
+      e4.x = ex2f(lam[0]); e4.y = ex2f(lam[1]); e4.z = ex2f(lam[2]); e4.w = ex2f(lam[3]);
+#pragma unroll
+      for (int w = 1; w < 4; ++w) {
+        const float rf = ref[w - 1];
+        v4[w - 1].x = ex2f(rf - lam[0]) * dtv[0]; v4[w - 1].y = ex2f(rf - lam[1]) * dtv[1];
+        v4[w - 1].z = ex2f(rf - lam[2]) * dtv[2]; v4[w - 1].w = ex2f(rf - lam[3]) * dtv[3];
+      }
+      // diagonal blocks: reference = cumsum just before the lane's own 32-token block (0 for the first block)
+      const float myref = lane < 8 ? 0.f : (lane < 16 ? ref[0] : (lane < 24 ? ref[1] : ref[2]));
+      vd4.x = ex2f(myref - lam[0]) * dtv[0]; vd4.y = ex2f(myref - lam[1]) * dtv[1];
+      vd4.z = ex2f(myref - lam[2]) * dtv[2]; vd4.w = ex2f(myref - lam[3]) * dtv[3];
+      const bool ok = __all_sync(0xffffffffu, myref - lam[3] < 100.f);
+      const float dchunk = ex2f(lam_last);
+      if (hh == 0) wait1(B_TAB_FREE + st, (n & 1) ^ 1);
+      named_bar_sync(7, 64);
       if (hh == 0) TR(9);
-      {
-        float4 l4 = make_float4(lam[0], lam[1], lam[2], lam[3]), d4 = make_float4(dtv[0], dtv[1], dtv[2], dtv[3]), s4, e4;
-        s4.x = ex2f(lam_last - lam[0]) * dtv[0]; s4.y = ex2f(lam_last - lam[1]) * dtv[1];
-        s4.z = ex2f(lam_last - lam[2]) * dtv[2]; s4.w = ex2f(lam_last - lam[3]) * dtv[3];
-        e4.x = ex2f(lam[0]); e4.y = ex2f(lam[1]); e4.z = ex2f(lam[2]); e4.w = ex2f(lam[3]);
-        reinterpret_cast<float4*>(tab->lam[hh])[lane] = l4;
-        reinterpret_cast<float4*>(tab->dtv[hh])[lane] = d4;
-        reinterpret_cast<float4*>(tab->sj[hh])[lane] = s4;
-        reinterpret_cast<float4*>(tab->eL[hh])[lane] = e4;
-#pragma unroll 1
-        for (int w = 1; w < 4; ++w)
-          if (lane < 8 * w) {
-            const float rf = ref[w - 1];
-            float4 v4;
-            v4.x = ex2f(rf - lam[0]) * dtv[0]; v4.y = ex2f(rf - lam[1]) * dtv[1];
-            v4.z = ex2f(rf - lam[2]) * dtv[2]; v4.w = ex2f(rf - lam[3]) * dtv[3];
-            reinterpret_cast<float4*>(tab->v[hh][w - 1])[lane] = v4;
-          }
-        // diagonal blocks: reference = cumsum just before the lane's own 32-token block (0 for the first block)
-        const float myref = lane < 8 ? 0.f : (lane < 16 ? ref[0] : (lane < 24 ? ref[1] : ref[2]));
-        float4 vd4;
-        vd4.x = ex2f(myref - lam[0]) * dtv[0]; vd4.y = ex2f(myref - lam[1]) * dtv[1];
-        vd4.z = ex2f(myref - lam[2]) * dtv[2]; vd4.w = ex2f(myref - lam[3]) * dtv[3];
-        reinterpret_cast<float4*>(tab->vd[hh])[lane] = vd4;
-        const bool ok = __all_sync(0xffffffffu, myref - lam[3] < 100.f);
-        if (lane == 0) {
-          tab->dchunk[hh] = ex2f(lam_last);
-          tab->safe[hh] = ok ? 1 : 0;
-        }
+      reinterpret_cast<float4*>(tab->lam[hh])[lane] = l4;
+      reinterpret_cast<float4*>(tab->dtv[hh])[lane] = d4;
+      reinterpret_cast<float4*>(tab->sj[hh])[lane] = s4;
+      reinterpret_cast<float4*>(tab->eL[hh])[lane] = e4;
+#pragma unroll
+      for (int w = 1; w < 4; ++w)
+        if (lane < 8 * w) reinterpret_cast<float4*>(tab->v[hh][w - 1])[lane] = v4[w - 1];
+      reinterpret_cast<float4*>(tab->vd[hh])[lane] = vd4;
+      if (lane == 0) {
+        tab->dchunk[hh] = dchunk;
+        tab->safe[hh] = ok ? 1 : 0;
       }
       __syncwarp();
       if (hh == 0) TR(10);
@@ -437,13 +480,13 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       it = itn;
     }
   } else if (warp < 12) {
-    // ============ x pass + P builders ==================================================================================
-    // x pass: lane = row i of head `sub`; P build: lane = row i, 32-column blocks split between the two warps of a quadrant
+    // ============ P builders (lane = row i, 32-column blocks split between the two warps of a quadrant) ==============
     const int pw = warp - 4, q = pw & 3, sub = pw >> 2, i = q * 32 + lane;
     // blocks of this warp, 4 bits per step (block index | 4 = diagonal block | 8 = zero-fill): (quadrant, sub) ->
     //   q3: {3d, 0} {1, 2}   q2: {2d} {0, 1, z3}   q1: {1d, z2} {0, z3}   q0: {0d} {z1, z2, z3}
     const uint32_t plan = sub == 0 ? (q == 3 ? 0xF07u : q == 2 ? 0xFF6u : q == 1 ? 0xFA5u : 0xFF4u)
                                    : (q == 3 ? 0xF21u : q == 2 ? 0xFB10u : q == 1 ? 0xFB0u : 0xFBA9u);
+    const int xw = pw;
     const uint32_t rx = (uint32_t)(i & 7) << 4;
     const uint32_t xrow = sub * 16384 + i * 128;  // byte offset of this lane's x row inside the XA / XB tiles
     ChunkIter it;
@@ -452,7 +495,11 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     for (uint32_t g = 0; g < total; ++g) {
       const uint32_t st = g & 1, n = g >> 1, ph = g & 1;
       const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
-      mbar_wait(&bars[B_TAB_READY + st], n & 1);
+      if (pw == 0) {
+        wait1(B_TAB_READY + st, n & 1);
+        if (mode == 0) wait1(B_CB_DONE, ph);
+      }
+      named_bar_sync(2, 256);
       if (mode == 0) {
       // ---- P build: P_h = CB o decay o dt (causal), fp16, written over CB in TMEM
       float lam_i[2], u_i[2];
@@ -462,7 +509,6 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         u_i[h] = ex2f(lam_i[h] - (q > 0 ? tab->lam[h][32 * q - 1] : 0.f));
       }
       const bool safe = tab->safe[0] != 0 && tab->safe[1] != 0;
-      mbar_wait(&bars[B_CB_DONE], ph);
       tc_fence_after();
       if (pw == 3) TR(12);
 #pragma unroll 1
@@ -530,16 +576,18 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       if (pw == 3) TR(13);
       if (lane == 0) mbar_arrive(&bars[B_P_READY]);
       }
-      // ---- x pass: x row -> fp16 in place (Ydiag operand), X' row -> XB (state operand), D x -> Ydiag accumulator
+      // ---- x pass (lane = row i of head `sub`): x row -> fp16 in place (Ydiag operand), X' row -> XB (state operand),
+      //      D x -> the head's Ydiag accumulator (released by the epilogue of the previous chunk: ACC_FREE per head)
+      if (xw == 0) {
+        if (g > 0) wait1(B_U_DONE, ph ^ 1);     // S-update(g-1) has read XB
+        wait1(B_FULL_X, ph);
+      }
+      if (q == 0 && mode == 0 && g > 0) wait1(B_ACC_FREE + sub, ph ^ 1);
+      named_bar_sync(3, 256);
+      if (mode == 0 && g > 0) tc_fence_after();
       const float sji = mode == 2 ? tab->eL[sub][i] : tab->sj[sub][i];  // (reverse sweep: dy rows scale by exp(lam_i))
       const float Dh = a.D ? ld_any(a.D, a.D_dtype, it.h0 + sub) : 0.f;
-      if (g > 0) {
-        mbar_wait(&bars[B_U_DONE], ph ^ 1);     // S-update(g-1) has read XB
-        if (mode == 0) mbar_wait(&bars[B_ACC_FREE], ph ^ 1);   // epilogue(g-1) has read the Ydiag accumulator
-        tc_fence_after();
-      }
-      mbar_wait(&bars[B_FULL_X], ph);
-      if (pw == 0) TR(17);
+      if (xw == 0) TR(17);
       {
         const float2 ss = make_float2(sji, sji), dd = make_float2(Dh, Dh);
 #pragma unroll 1
@@ -571,45 +619,115 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (pw == 0) TR(18);
+      if (xw == 0) TR(18);
       if (lane == 0) {
         mbar_arrive(&bars[B_X16_READY]);
-        mbar_arrive(&bars[B_TAB_FREE + st]);
+        if (mode == 0) mbar_arrive(&bars[B_DX_READY + sub]);
       }
-
+      if (lane == 0) mbar_arrive(&bars[B_TAB_FREE + st]);
       it_next(it);
     }
   } else {
-    // ============ state keepers (TMEM lane r = (head, p)) + epilogue (lane = row i) ==================================
+    // ============ epilogue (lane = row i) + state keepers (TMEM lane r = (head, p)) ==================================
     const int w = warp - 12, r = w * 32 + lane, hh = r >> 6, p = r & 63;
     const uint32_t rx = (uint32_t)(r & 7) << 4;
-    uint8_t* ybuf = smem + SM_Y + w * 4096;
+    uint8_t* ybuf = smem + SM_Y + w * 4096;   // two 2 KB slots: [32 rows x 64 B] = 32 columns of one head, 64B swizzle
     ChunkIter sn, ep;  // chunk gg (state step) and chunk gg - 1 (epilogue)
     it_set(sn, blockIdx.x);
     ep = sn;
-    // iteration gg = 0 .. total: [state step of chunk gg] then [epilogue of chunk gg - 1]
+    int fin_b = 0, fin_h0 = 0;  // item of the chunk whose epilogue slot ran last (owner of the state at an item boundary)
+    // iteration gg = 0 .. total: [epilogue of chunk gg - 1] then [state step of chunk gg].  The epilogue comes first: it is
+    // on the chunk-to-chunk critical path (it frees the accumulators), the state step has slack until Yoff(gg).
 #pragma unroll 1
     for (uint32_t gg = 0; gg < total + 1; ++gg) {
+      if (gg > 0 && mode == 0) {
+        // ---- epilogue(g = gg - 1): y = Ydiag (+ D x) + exp(lam_i) Yoff, row i = r
+        const uint32_t g = gg - 1;
+        const uint32_t st = g & 1, ph = g & 1;
+        const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
+        const float eL0 = tab->eL[0][r], eL1 = tab->eL[1][r];
+        if (w == 0) wait1(B_YD_DONE, ph);   // Yoff(g) was issued before Ydiag(g): complete as well
+        named_bar_sync(6, 128);
+        tc_fence_after();
+        if (w == 0) TR(19);
+        const int eb = ep.b, eh0 = ep.h0, ec = ep.c;
+        const int t = ec * Q + r;
+#pragma unroll 1
+        for (int s4 = 0; s4 < 4; ++s4) {  // s4 = head * 2 + 32-column half
+          const int hx = s4 >> 1, half = s4 & 1;
+          uint8_t* slot = ybuf + half * 2048;
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tmem_addr(tb, w * 32, TM_YOFF + 32 * s4), v0);
+          tmem_ld32(tmem_addr(tb, w * 32, TM_YD + 32 * s4), v1);
+          if (a.out_dtype == OMNI_BF16) {  // the slot is free once the store issued two steps ago has read it
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          const float eh = hx == 0 ? eL0 : eL1;
+          const float2 ee = make_float2(eh, eh);
+          float2 y[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) y[e] = fma2(u2f2(v0[2 * e], v0[2 * e + 1]), ee, u2f2(v1[2 * e], v1[2 * e + 1]));
+          if (half == 1) {  // both accumulators of this head have been read
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&bars[B_ACC_FREE + hx]);
+              if (hx == 1) mbar_arrive(&bars[B_TAB_FREE + st]);
+            }
+          }
+          if (a.out_dtype == OMNI_BF16) {
+            uint8_t* yrow = slot + lane * 64;
+            const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(yrow + (((uint32_t)k ^ sw) << 4)) =
+                  make_uint4(pack_bf16(y[4 * k].x, y[4 * k].y), pack_bf16(y[4 * k + 1].x, y[4 * k + 1].y),
+                             pack_bf16(y[4 * k + 2].x, y[4 * k + 2].y), pack_bf16(y[4 * k + 3].x, y[4 * k + 3].y));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && ec * Q + w * 32 < a.L) {  // rows beyond L are clipped by the tensor map
+              tma_store_4d(&mapY, slot, 32 * half, eh0 + hx, ec * Q + w * 32, eb);
+              tma_store_commit();
+            }
+          } else if (t < a.L) {  // fp32 output (parity tests): straight to HBM
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(a.out) + eb * a.o_b + (int64_t)t * a.o_l +
+                                                    (int64_t)(eh0 + hx) * a.o_h + 32 * half);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[k] = make_float4(y[2 * k].x, y[2 * k].y, y[2 * k + 1].x, y[2 * k + 1].y);
+          }
+          if (w == 0 && s4 < 3) TR(23 + s4);
+        }
+        if (w == 0) TR(22);
+      }
+      if (gg > 0) {
+        fin_b = ep.b; fin_h0 = ep.h0;
+        it_next(ep);
+      }
       if (gg < total) {
         // ---- S16 = fp16(S) for Yoff(gg);  S <- exp(lam_last(gg)) S  (initial state on the first chunk of an item)
         const uint32_t g = gg;  // (for the trace macro)
         const uint32_t st = gg & 1, n = gg >> 1;
         const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
-        mbar_wait(&bars[B_TAB_READY + st], n & 1);
+        if (w == 0) {
+          wait1(B_TAB_READY + st, n & 1);
+          if (gg > 0) {
+            if (mode == 0) wait1(B_YOFF_DONE, (gg - 1) & 1);  // Yoff(gg-1) has read the S16 tile
+            wait1(B_U_DONE, (gg - 1) & 1);     // S-update(gg-1) is complete
+          }
+        }
+        named_bar_sync(6, 128);
         const float dch = tab->dchunk[hh];
         if (mode != 0) {  // state sweeps: the previous TMA store must have read the S16 tile
           if (w == 0 && lane == 0) tma_store_wait_read<0>();
           named_bar_sync(1, 128);
         }
-        if (gg > 0) {
-          if (mode == 0) mbar_wait(&bars[B_YOFF_DONE], (gg - 1) & 1);  // Yoff(gg-1) has read the S16 tile
-          mbar_wait(&bars[B_U_DONE], (gg - 1) & 1);     // S-update(gg-1) is complete
-          tc_fence_after();
-        }
+        if (gg > 0) tc_fence_after();
         if (w == 0) TR(15);
         if (sn.c == 0) {
           if (gg > 0 && a.fin) {  // final state of the item that just ended (the item of chunk gg - 1)
-            float* dst = a.fin + ((int64_t)(ep.b * a.H + ep.h0 + hh) * HD + p) * NS;
+            float* dst = a.fin + ((int64_t)(fin_b * a.H + fin_h0 + hh) * HD + p) * NS;
 #pragma unroll 1
             for (int k4 = 0; k4 < 4; ++k4) {
               uint32_t v[32];
@@ -676,73 +794,9 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         it_next(sn);
       }
-      if (gg == 0) continue;
-      if (mode != 0) {
-        it_next(ep);
-        continue;
-      }
-      // ---- epilogue(g = gg - 1): y = Ydiag (+ D x) + exp(lam_i) Yoff, row i = r
-      const uint32_t g = gg - 1;
-      const uint32_t st = g & 1, ph = g & 1;
-      const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
-      const float eL0 = tab->eL[0][r], eL1 = tab->eL[1][r];
-      mbar_wait(&bars[B_YD_DONE], ph);   // Ydiag(g) is the last MMA of chunk g: Yoff(g) is complete as well
-      tc_fence_after();
-      if (w == 0) TR(19);
-      const int eb = ep.b, eh0 = ep.h0, ec = ep.c;
-      const int t = ec * Q + r;
-#pragma unroll 1
-      for (int s4 = 0; s4 < 4; ++s4) {  // s4 = head * 2 + 32-column half
-        const int hx = s4 >> 1, half = s4 & 1;
-        if (half == 0 && a.out_dtype == OMNI_BF16) {  // the staging tile is free once the previous TMA store has read it
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
-        }
-        uint32_t v0[32], v1[32];
-        tmem_ld32(tmem_addr(tb, w * 32, TM_YOFF + 32 * s4), v0);
-        tmem_ld32(tmem_addr(tb, w * 32, TM_YD + 32 * s4), v1);
-        tmem_ld_wait();
-        const float eh = hx == 0 ? eL0 : eL1;
-        const float2 ee = make_float2(eh, eh);
-        float2 y[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) y[e] = fma2(u2f2(v0[2 * e], v0[2 * e + 1]), ee, u2f2(v1[2 * e], v1[2 * e + 1]));
-        if (a.out_dtype == OMNI_BF16) {
-          uint8_t* yrow = ybuf + lane * 128;
-          const uint32_t lx = (uint32_t)(lane & 7) << 4, c0 = (uint32_t)half << 6;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<uint4*>(yrow + ((c0 + ((uint32_t)k << 4)) ^ lx)) =
-                make_uint4(pack_bf16(y[4 * k].x, y[4 * k].y), pack_bf16(y[4 * k + 1].x, y[4 * k + 1].y),
-                           pack_bf16(y[4 * k + 2].x, y[4 * k + 2].y), pack_bf16(y[4 * k + 3].x, y[4 * k + 3].y));
-        } else if (t < a.L) {  // fp32 output (parity tests): straight to HBM
-          float4* dst = reinterpret_cast<float4*>(static_cast<float*>(a.out) + eb * a.o_b + (int64_t)t * a.o_l +
-                                                  (int64_t)(eh0 + hx) * a.o_h + 32 * half);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) dst[k] = make_float4(y[2 * k].x, y[2 * k].y, y[2 * k + 1].x, y[2 * k + 1].y);
-        }
-        if (s4 == 3) {  // both accumulators have been read
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&bars[B_ACC_FREE]);
-            mbar_arrive(&bars[B_TAB_FREE + st]);
-          }
-        }
-        if (half == 1 && a.out_dtype == OMNI_BF16) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && ec * Q + w * 32 < a.L) {  // rows beyond L are clipped by the tensor map
-            tma_store_4d(&mapY, ybuf, 0, eh0 + hx, ec * Q + w * 32, eb);
-            tma_store_commit();
-          }
-        }
-      }
-      if (w == 0) TR(22);
-      it_next(ep);
     }
     if (total > 0 && a.fin) {  // final state of the last item
-      mbar_wait(&bars[B_U_DONE], (total - 1) & 1);
+      wait1(B_U_DONE, (total - 1) & 1);
       tc_fence_after();
       ChunkIter fl;
       it_set(fl, blockIdx.x + (my_items - 1) * gridDim.x);
@@ -903,7 +957,12 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   if (int rc = tmap4(&mB, wsB, bc_shape, bc_stride, false, Q)) return rc;
   if (int rc = tmap4(&mC, wsC ? wsC : wsB, bc_shape, bc_stride, false, Q)) return rc;
   if (mode == 0 && o.dtype == OMNI_BF16) {  // y leaves through per-warp TMA stores of 32 rows
-    if (int rc = tmap4(&mY, o.data, o.shape, o.stride, true, 32)) return rc;
+    // y leaves through per-warp TMA stores of 32 rows x 32 columns (64B swizzle)
+    const uint64_t dims[4] = {(uint64_t)o.shape[3], (uint64_t)o.shape[2], (uint64_t)o.shape[1], (uint64_t)o.shape[0]};
+    auto st = [&](int d) { return (uint64_t)(o.shape[d] > 1 ? o.stride[d] : o.shape[3]) * 2; };
+    const uint64_t strides[3] = {st(2), st(1), st(0)};
+    const uint32_t box[4] = {32, 1, 32, 1};
+    if (int rc = make_tmap_16bit(&mY, o.data, 4, dims, strides, box, true, 64)) return rc;
   } else {
     mY = mX;  // unused
   }

@@ -193,7 +193,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();  // nullptr if the driver does not export it
 
 // bf16/fp16 tensor, `rank` dims (innermost first), strides in BYTES for dims 1..rank-1, 128B swizzle.
+// `swizzle` = 128 (default), 64 or 0 (none): the inner box must not exceed the swizzle span.
 int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, bool is_bf16);
+                    const uint32_t* box, bool is_bf16, int swizzle = 128);
 
 }  // namespace omni

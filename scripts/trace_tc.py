@@ -11,9 +11,9 @@ sys.path.insert(0, ROOT)
 from omnimamba_b200 import _cabi  # noqa: E402
 from omnimamba_b200.interface.ssd_combined import ssd_fwd_raw  # noqa: E402
 
-NAMES = {0: "tma:x_issue(g+1)", 1: "tma:B_issue(g+2)", 2: "tma:C_issue(g+1)", 3: "mma:CB", 4: "mma:Yoff", 5: "mma:U", 6: "mma:Yd",
-         8: "tab:start", 9: "tab:free", 10: "tab:ready", 12: "P:cb_done", 13: "P:done", 15: "S:u_done(g-1)",
-         16: "S:s_ready", 17: "X:full_x", 18: "X:x16_ready", 19: "E:yd_done", 22: "E:stored"}
+NAMES = {0: "tma:x_issue(g+1)", 1: "tma:B_issue(g+2)", 2: "tma:C_issue(g+1)", 3: "mma:CB(g+1)", 4: "mma:Yoff", 5: "mma:U", 6: "mma:Yd",
+         8: "tab:start", 9: "tab:free", 10: "tab:ready", 12: "P:cb_done", 13: "P:done", 14: "X:dx_ready", 15: "S:u_done(g-1)",
+         16: "S:s_ready", 17: "X:full_x", 18: "X:x16_ready", 19: "E:acc_done", 22: "E:stored", 23: "E:s4=0", 24: "E:s4=1", 25: "E:s4=2"}
 
 
 def main():
