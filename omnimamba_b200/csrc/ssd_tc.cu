@@ -46,6 +46,9 @@ using namespace umma;
 constexpr int Q = 128;     // tokens per chunk
 constexpr int HD = 64;     // headdim
 constexpr int NS = 128;    // d_state
+// Warps that watch mbarriers for their role sit on schedulers 2 and 3 (with the TMA / MMA threads); the table warps (0, 1),
+// whose serial dt -> cumsum -> exp chain feeds every chunk, share their schedulers with no spinning warp.
+constexpr int kLeadPX = 2, kLeadE = 3;
 constexpr int kThreads = 512;   // 16 warps: 2 table, TMA, MMA, 8 P build + x pass, 4 epilogue + state
 
 // shared-memory map (bytes, relative to the 1024B-aligned base)
@@ -74,7 +77,10 @@ enum {
   B_FULL_C = 8, B_FULL_X, B_CB_DONE, B_P_READY, B_X16_READY, B_S_READY, B_YOFF_DONE, B_U_DONE, B_YD_DONE,
   B_ACC_FREE = 17,  // [head 2] epilogue has read both accumulators of the head
   B_DX_READY = 19,  // [head 2] x pass part (b): D x is in the head's Ydiag accumulator
-  B_COUNT = 21
+  // state sweeps (modes 1 / 2): x-like tiles rotate through three stages (XA, XB and the C slot, all unused otherwise)
+  B_SW_FULL = 21,   // [stage 3] TMA tile landed
+  B_SW_XR = 24,     // [stage 3] the x pass has scaled the tile in place
+  B_COUNT = 27
 };
 constexpr uint32_t SM_TMEMPTR = SM_BAR + B_COUNT * 8;
 constexpr uint32_t SM_TOTAL = SM_TMEMPTR + 16;
@@ -178,6 +184,10 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       mbar_init(&bars[B_ACC_FREE + i], 4);
       mbar_init(&bars[B_DX_READY + i], 4);
     }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bars[B_SW_FULL + i], 1);
+      mbar_init(&bars[B_SW_XR + i], 8);
+    }
     mbar_init(&bars[B_FULL_C], 1);
     mbar_init(&bars[B_FULL_X], 1);
     mbar_init(&bars[B_CB_DONE], 1);
@@ -254,6 +264,38 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         tma_prefetch_4d(&mapX, 0, it.h0, cphys(it.c) * Q, it.b);
         tma_prefetch_4d(&mapX, 0, it.h0 + 1, cphys(it.c) * Q, it.b);
       };
+      if (mode != 0) {
+        // state sweeps: B two chunks ahead (two stages), the x-like tile three chunks ahead (three stages); the state
+        // update of chunk g releases B stage g & 1 and tile stage g % 3
+        auto load_xs = [&](const ChunkIter& it, uint32_t s3) {
+          uint8_t* dst = smem + (s3 == 0 ? SM_XA : s3 == 1 ? SM_XB : SM_C);
+          mbar_expect_tx(&bars[B_SW_FULL + s3], 32768);
+          tma_load_4d(dst, &mapX, &bars[B_SW_FULL + s3], 0, it.h0, cphys(it.c) * Q, it.b);
+          tma_load_4d(dst + 16384, &mapX, &bars[B_SW_FULL + s3], 0, it.h0 + 1, cphys(it.c) * Q, it.b);
+        };
+        ChunkIter itb, itx;
+        it_set(itb, blockIdx.x);
+        itx = itb;
+        for (uint32_t k = 0; k < 3 && k < total; ++k) {
+          if (k < 2) { load_b(itb, k); it_next(itb); }
+          load_xs(itx, k);
+          it_next(itx);
+        }
+        uint32_t s3 = 0;
+#pragma unroll 1
+        for (uint32_t g = 0; g + 2 < total; ++g) {
+          wait1(B_EMPTY_B + (g & 1), (g >> 1) & 1);  // S-update(g) has read B stage g & 1 and tile stage g % 3
+          TR(1);
+          load_b(itb, g & 1);
+          it_next(itb);
+          if (g + 3 < total) {
+            TR(0);
+            load_xs(itx, s3);
+            it_next(itx);
+          }
+          if (++s3 == 3) s3 = 0;
+        }
+      } else {
       ChunkIter it1, it2;  // chunks g + 1 and g + 2
       it_set(it1, blockIdx.x);
       if (mode == 0) load_c(it1);
@@ -282,6 +324,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         it_next(it1);
         it_next(it2);
       }
+      }
     }
   } else if (warp == 3) {
     // ============ MMA issuer ==========================================================================================
@@ -299,13 +342,16 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const uint32_t st = g & 1, n = g >> 1, ph = g & 1;
         const uint64_t dBk = make_sdesc(smem_u32(smem + SM_B + st * 32768), 16, 1024);
         const uint64_t dBm = make_sdesc(smem_u32(smem + SM_B + st * 32768), 16384, 1024);
-        if (mode != 0) {  // state sweeps: only the state update
+        if (mode != 0) {  // state sweeps: only the state update, A operand = tile stage g % 3 (scaled in place)
+          const uint32_t s3 = g % 3, k3 = (g / 3) & 1;
+          const uint64_t dXs = make_sdesc(smem_u32(smem + (s3 == 0 ? SM_XA : s3 == 1 ? SM_XB : SM_C)), 16384, 1024);
           wait1(B_FULL_B + st, n & 1);
           wait1(B_S_READY, ph);
-          wait1(B_X16_READY, ph);
+          wait1(B_SW_XR + s3, k3);
           tc_fence_after();
-#pragma unroll 1
-          for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + TM_S, dXB + k * 128, dBm + k * 128, id_u, true);
+          TR(5);
+#pragma unroll
+          for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + TM_S, dXs + k * 128, dBm + k * 128, id_u, true);
           mma_commit(&bars[B_U_DONE]);
           mma_commit(&bars[B_EMPTY_B + st]);
           continue;
@@ -380,37 +426,63 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
   } else if (warp < 2) {
     // ============ table warps (one head each): dt transform, decay cumsum, exp tables ================================
+    // One lane = 4 consecutive tokens.  dt rows are 2-byte gathers with a token stride: an HBM miss costs ~2500 cycles, more
+    // than a state-sweep chunk takes, so the lines are pulled into L2 three chunks ahead and the register load (one chunk
+    // ahead) becomes an L2 hit.  Addresses are byte offsets advanced per chunk; per-head constants are reloaded per item.
     const int hh = warp;
-    uint32_t raw[4];  // raw dt bits of the NEXT chunk: loaded a chunk ahead, converted only when used
-    auto load_raw = [&](const ChunkIter& it, bool valid) {
-      const int64_t base = it.b * a.dt_b + (int64_t)(it.h0 + hh) * a.dt_h;
+    const int esz = a.dt_dtype == OMNI_F32 ? 4 : 2;
+    const int64_t tstride = a.dt_l * esz;  // bytes between consecutive tokens
+    const char* dtbase = static_cast<const char*>(a.dt);
+    auto chunk_ptr = [&](const ChunkIter& it) -> const char* {  // this lane's first token of the chunk
+      return dtbase + (it.b * a.dt_b + (int64_t)(it.h0 + hh) * a.dt_h) * esz + (int64_t)(cphys(it.c) * Q + lane * 4) * tstride;
+    };
+    // raw dt bits are loaded TWO chunks ahead into two statically alternating register sets (the loop is unrolled by two)
+    uint32_t raw_a[4], raw_b[4];
+    auto load_raw = [&](uint32_t (&raw)[4], const ChunkIter& it, bool valid) {
+      const char* ptr = chunk_ptr(it);
+      const int t0 = cphys(it.c) * Q + lane * 4;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int t = cphys(it.c) * Q + lane * 4 + k;
         raw[k] = 0u;
-        if (valid && t < a.L) {
-          if (a.dt_dtype == OMNI_F32) raw[k] = __ldg(static_cast<const uint32_t*>(a.dt) + base + (int64_t)t * a.dt_l);
-          else raw[k] = __ldg(static_cast<const unsigned short*>(a.dt) + base + (int64_t)t * a.dt_l);
+        if (valid && t0 + k < a.L) {
+          if (esz == 4) raw[k] = __ldg(reinterpret_cast<const uint32_t*>(ptr + k * tstride));
+          else raw[k] = __ldg(reinterpret_cast<const unsigned short*>(ptr + k * tstride));
         }
       }
+    };
+    auto prefetch_raw = [&](const ChunkIter& it) {
+      const char* ptr = chunk_ptr(it);
+      const int t0 = cphys(it.c) * Q + lane * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t0 + k < a.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + k * tstride));
     };
     auto raw_to_f = [&](uint32_t bits) -> float {
       if (a.dt_dtype == OMNI_F32) return __uint_as_float(bits);
       if (a.dt_dtype == OMNI_BF16) return __uint_as_float(bits << 16);
       return __half2float(__ushort_as_half((unsigned short)bits));
     };
-    ChunkIter it, itn;
+    ChunkIter it, itn, itp;
     it_set(it, blockIdx.x);
     itn = it;
-    load_raw(it, total > 0);
-#pragma unroll 1
-    for (uint32_t g = 0; g < total; ++g) {
-      const int h = it.h0 + hh, c = cphys(it.c);
+    load_raw(raw_a, itn, total > 0);
+    it_next(itn);
+    load_raw(raw_b, itn, total > 1);
+    itp = itn;
+    for (uint32_t k = 2; k <= 4 && k < total; ++k) {
+      it_next(itp);
+      prefetch_raw(itp);
+    }
+    float Ah2 = 0.f, bias = 0.f;
+    auto body = [&](uint32_t (&raw)[4], uint32_t g) {
+      const int c = cphys(it.c);
       const uint32_t st = g & 1, n = g >> 1;
       Tab* tab = reinterpret_cast<Tab*>(smem + SM_TAB) + st;
       if (hh == 0) TR(8);
-      const float Ah2 = a.A[h] * 1.4426950408889634f;
-      const float bias = a.dt_bias ? ld_any(a.dt_bias, a.dtb_dtype, h) : 0.f;
+      if (it.c == 0) {  // new item: per-head constants
+        Ah2 = a.A[it.h0 + hh] * 1.4426950408889634f;
+        bias = a.dt_bias ? ld_any(a.dt_bias, a.dtb_dtype, it.h0 + hh) : 0.f;
+      }
       float dtv[4], lam[4];
       float run = 0.f;
 #pragma unroll
@@ -427,7 +499,11 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         lam[k] = run;
       }
       it_next(itn);
-      load_raw(itn, g + 1 < total);  // next chunk's raw dt: in flight while this chunk's tables are built
+      load_raw(raw, itn, g + 2 < total);  // raw dt of chunk g + 2 (this register set's next use)
+      if (g + 5 < total) {
+        it_next(itp);
+        prefetch_raw(itp);
+      }
       float incl = run;  // warp inclusive scan of the per-lane totals (Hillis-Steele)
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -438,6 +514,23 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
       for (int k = 0; k < 4; ++k) lam[k] += excl;
       const float lam_last = __shfl_sync(0xffffffffu, lam[3], 31);
+      const float dchunk = ex2f(lam_last);
+      if (mode != 0) {
+        // state sweeps: only the row scale of the x-like tile (sj forward, exp(lam_i) reverse) and the chunk decay
+        float4 r4;
+        if (mode == 1) {
+          r4.x = ex2f(lam_last - lam[0]) * dtv[0]; r4.y = ex2f(lam_last - lam[1]) * dtv[1];
+          r4.z = ex2f(lam_last - lam[2]) * dtv[2]; r4.w = ex2f(lam_last - lam[3]) * dtv[3];
+        } else {
+          r4.x = ex2f(lam[0]); r4.y = ex2f(lam[1]); r4.z = ex2f(lam[2]); r4.w = ex2f(lam[3]);
+        }
+        if (hh == 0) wait1(B_TAB_FREE + st, (n & 1) ^ 1);
+        named_bar_sync(7, 64);
+        if (hh == 0) TR(9);
+        if (mode == 1) reinterpret_cast<float4*>(tab->sj[hh])[lane] = r4;
+        else reinterpret_cast<float4*>(tab->eL[hh])[lane] = r4;
+        if (lane == 0) tab->dchunk[hh] = dchunk;
+      } else {
       float ref[3];
 #pragma unroll
       for (int w = 1; w < 4; ++w) ref[w - 1] = __shfl_sync(0xffffffffu, lam[3], 8 * w - 1);
@@ -458,7 +551,6 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       vd4.x = ex2f(myref - lam[0]) * dtv[0]; vd4.y = ex2f(myref - lam[1]) * dtv[1];
       vd4.z = ex2f(myref - lam[2]) * dtv[2]; vd4.w = ex2f(myref - lam[3]) * dtv[3];
       const bool ok = __all_sync(0xffffffffu, myref - lam[3] < 100.f);
-      const float dchunk = ex2f(lam_last);
       if (hh == 0) wait1(B_TAB_FREE + st, (n & 1) ^ 1);
       named_bar_sync(7, 64);
       if (hh == 0) TR(9);
@@ -474,10 +566,16 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         tab->dchunk[hh] = dchunk;
         tab->safe[hh] = ok ? 1 : 0;
       }
+      }
       __syncwarp();
       if (hh == 0) TR(10);
       if (lane == 0) mbar_arrive(&bars[B_TAB_READY + st]);
-      it = itn;
+      it_next(it);
+    };
+#pragma unroll 1
+    for (uint32_t g = 0; g < total; g += 2) {
+      body(raw_a, g);
+      if (g + 1 < total) body(raw_b, g + 1);
     }
   } else if (warp < 12) {
     // ============ P builders (lane = row i, 32-column blocks split between the two warps of a quadrant) ==============
@@ -495,12 +593,41 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     for (uint32_t g = 0; g < total; ++g) {
       const uint32_t st = g & 1, n = g >> 1, ph = g & 1;
       const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
-      if (pw == 0) {
+      if (mode != 0) {
+        // state sweeps: scale the x-like tile of stage g % 3 in place (rows x sj, or dy rows x exp(lam_i) in the reverse
+        // sweep); the stage belongs to this chunk until its state update has read it, so nothing else to wait for
+        const uint32_t s3 = g % 3, k3 = (g / 3) & 1;
+        uint8_t* tile = smem + (s3 == 0 ? SM_XA : s3 == 1 ? SM_XB : SM_C);
+        if (pw == kLeadPX) {
+          wait1(B_TAB_READY + st, n & 1);
+          wait1(B_SW_FULL + s3, k3);
+        }
+        named_bar_sync(2, 256);
+        if (pw == 0) TR(17);
+        const float sjs = mode == 2 ? tab->eL[sub][i] : tab->sj[sub][i];
+        const float2 ss = make_float2(sjs, sjs);
+#pragma unroll 4
+        for (int k8 = 0; k8 < 8; ++k8) {
+          uint4* ptr = reinterpret_cast<uint4*>(tile + xrow + (((uint32_t)k8 << 4) ^ rx));
+          const uint4 v = *ptr;
+          const float2 s0 = mul2(bf2f2(v.x), ss), s1 = mul2(bf2f2(v.y), ss), s2 = mul2(bf2f2(v.z), ss), s3v = mul2(bf2f2(v.w), ss);
+          *ptr = make_uint4(pack_f16_sat(s0.x, s0.y), pack_f16_sat(s1.x, s1.y), pack_f16_sat(s2.x, s2.y), pack_f16_sat(s3v.x, s3v.y));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (pw == 0) TR(18);
+        if (lane == 0) {
+          mbar_arrive(&bars[B_SW_XR + s3]);
+          mbar_arrive(&bars[B_TAB_FREE + st]);
+        }
+        continue;
+      }
+      if (pw == kLeadPX) {
         wait1(B_TAB_READY + st, n & 1);
-        if (mode == 0) wait1(B_CB_DONE, ph);
+        wait1(B_CB_DONE, ph);
       }
       named_bar_sync(2, 256);
-      if (mode == 0) {
+      {
       // ---- P build: P_h = CB o decay o dt (causal), fp16, written over CB in TMEM
       float lam_i[2], u_i[2];
 #pragma unroll
@@ -578,11 +705,11 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       }
       // ---- x pass (lane = row i of head `sub`): x row -> fp16 in place (Ydiag operand), X' row -> XB (state operand),
       //      D x -> the head's Ydiag accumulator (released by the epilogue of the previous chunk: ACC_FREE per head)
-      if (xw == 0) {
+      if (xw == kLeadPX) {
         if (g > 0) wait1(B_U_DONE, ph ^ 1);     // S-update(g-1) has read XB
         wait1(B_FULL_X, ph);
       }
-      if (q == 0 && mode == 0 && g > 0) wait1(B_ACC_FREE + sub, ph ^ 1);
+      if (q == kLeadPX && mode == 0 && g > 0) wait1(B_ACC_FREE + sub, ph ^ 1);
       named_bar_sync(3, 256);
       if (mode == 0 && g > 0) tc_fence_after();
       const float sji = mode == 2 ? tab->eL[sub][i] : tab->sj[sub][i];  // (reverse sweep: dy rows scale by exp(lam_i))
@@ -646,7 +773,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const uint32_t st = g & 1, ph = g & 1;
         const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
         const float eL0 = tab->eL[0][r], eL1 = tab->eL[1][r];
-        if (w == 0) wait1(B_YD_DONE, ph);   // Yoff(g) was issued before Ydiag(g): complete as well
+        if (w == kLeadE) wait1(B_YD_DONE, ph);   // Yoff(g) was issued before Ydiag(g): complete as well
         named_bar_sync(6, 128);
         tc_fence_after();
         if (w == 0) TR(19);
@@ -710,7 +837,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const uint32_t g = gg;  // (for the trace macro)
         const uint32_t st = gg & 1, n = gg >> 1;
         const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
-        if (w == 0) {
+        if (w == kLeadE) {
           wait1(B_TAB_READY + st, n & 1);
           if (gg > 0) {
             if (mode == 0) wait1(B_YOFF_DONE, (gg - 1) & 1);  // Yoff(gg-1) has read the S16 tile
@@ -845,6 +972,7 @@ __global__ void __launch_bounds__(256) ssd_tc_prep_kernel(PrepArgs a) {
 
 long long* g_trace = nullptr;
 int g_trace_chunks = 0;
+int g_trace_mode = 0;  // which launch mode records (0 forward, 1 / 2 state sweeps)
 
 bool tmap_stride_ok(int64_t elems) { return elems >= 0 && (elems * 2) % 16 == 0; }
 
@@ -941,7 +1069,7 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   }
   a.B = (int)Bsz; a.L = (int)L; a.H = (int)H; a.G = (int)G;
   a.dt_softplus = dt_softplus; a.dt_min = dt_min; a.dt_max = dt_max;
-  a.trace = mode == 0 ? g_trace : nullptr; a.trace_chunks = g_trace_chunks;
+  a.trace = mode == g_trace_mode ? g_trace : nullptr; a.trace_chunks = g_trace_chunks;
 
   auto tmap4 = [&](CUtensorMap* m, const void* base, const int64_t* shape, const int64_t* stride, bool bf16, int rows) -> int {
     // dims innermost first: (inner, dim2, L, B); a size-1 dim may carry any stride: give TMA a harmless legal one
@@ -1020,7 +1148,8 @@ extern "C" void omni_debug_set_mbar_hint(unsigned ns) { cudaMemcpyToSymbol(omni:
 // debug: CTA 0 of the next ssd_tc launches records clock64() per (chunk, event) into buf[chunks * 32] (device int64)
 extern "C" void omni_debug_set_trace(void* buf, int chunks) {
   omni::g_trace = static_cast<long long*>(buf);
-  omni::g_trace_chunks = chunks;
+  omni::g_trace_mode = chunks / 1000;  // (debug convention: chunks = 1000 * mode + number of chunks)
+  omni::g_trace_chunks = chunks % 1000;
 }
 
 // bytes of caller-provided workspace the tensor-core forward needs (fp16 copies of B and C)
