@@ -103,17 +103,29 @@ __global__ void __launch_bounds__(32 * kWarps) ssu_kernel(SsuArgs a) {
       if (p < a.P && nvalid[j]) ld4<TS>(sbase + p * a.st_p + n, S[r][j]);
     }
   }
+  // per-row scalars of all rows first: their (dependent-free) loads are in flight together with the state rows instead of
+  // costing one memory latency per row
+  float dtr[kRows], xr[kRows], Ar[kRows], Dr[kRows], zr[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    const int p = min(p0 + r, a.P - 1);
+    dtr[r] = ld_any(a.dt, a.dt_dtype, b * a.dt_b + h * a.dt_h + p * a.dt_p);
+    if (a.dt_bias) dtr[r] += ld_any(a.dt_bias, a.db_dtype, h * a.db_h + p * a.db_p);
+    xr[r] = ld_any(a.x, a.x_dtype, b * a.x_b + h * a.x_h + p * a.x_p);
+    Ar[r] = TIE_A ? ld_any(a.A, a.A_dtype, h * a.A_h + p * a.A_p) : 0.f;
+    Dr[r] = a.D ? ld_any(a.D, a.D_dtype, h * a.D_h + p * a.D_p) : 0.f;
+    zr[r] = a.z ? ld_any(a.z, a.x_dtype, b * a.z_b + h * a.z_h + p * a.z_p) : 0.f;
+  }
 #pragma unroll
   for (int r = 0; r < kRows; ++r) {
     const int p = p0 + r;
     if (p >= a.P) continue;  // warp-uniform
-    float dtv = ld_any(a.dt, a.dt_dtype, b * a.dt_b + h * a.dt_h + p * a.dt_p);
-    if (a.dt_bias) dtv += ld_any(a.dt_bias, a.db_dtype, h * a.db_h + p * a.db_p);
+    float dtv = dtr[r];
     if (a.dt_softplus) dtv = softplus_f(dtv);
-    const float xv = ld_any(a.x, a.x_dtype, b * a.x_b + h * a.x_h + p * a.x_p);
+    const float xv = xr[r];
     const float dtx = dtv * xv;
     float dA_tied = 0.f;
-    if (TIE_A) dA_tied = __expf(dtv * ld_any(a.A, a.A_dtype, h * a.A_h + p * a.A_p));
+    if (TIE_A) dA_tied = __expf(dtv * Ar[r]);
     float acc = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -131,8 +143,8 @@ __global__ void __launch_bounds__(32 * kWarps) ssu_kernel(SsuArgs a) {
     }
     acc = warp_sum(acc);
     if (lane == 0) {
-      if (a.D) acc += xv * ld_any(a.D, a.D_dtype, h * a.D_h + p * a.D_p);
-      if (a.z) acc *= silu_f(ld_any(a.z, a.x_dtype, b * a.z_b + h * a.z_h + p * a.z_p));
+      if (a.D) acc += xv * Dr[r];
+      if (a.z) acc *= silu_f(zr[r]);
       st_any(a.out, a.x_dtype, b * a.o_b + h * a.o_h + p * a.o_p, acc);
     }
   }

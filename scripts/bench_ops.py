@@ -1,0 +1,103 @@
+"""HBM roofline of the other hot-path rows of SURVEY.md 8(a) at d_model=2048 (run on the GPU box):
+
+    python scripts/bench_ops.py > gpurun_out/bench_ops.json
+
+Each op is called through the public operator surface on device-resident tensors larger than L2 (or with an L2 flush
+between iterations for the small decode tensors), timed with CUDA events on the launch stream; `achieved` = ALGORITHMIC
+bytes / time against MEASURED_PEAKS.json hbm_gbs.  One JSON object per line.
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from omnimamba_b200.interface import causal_conv1d_fn, causal_conv1d_update, selective_state_update  # noqa: E402
+from omnimamba_b200.interface.layer_norm import layer_norm_fn  # noqa: E402
+from omnimamba_b200.interface.layernorm_gated import rmsnorm_fn  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def timeit(fn, steps=20, warmup=5, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(steps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / steps / 1e3
+
+
+def main():
+    dev = "cuda"
+    hbm = peak()
+    g = torch.Generator(device=dev).manual_seed(0)
+    rn = lambda *s, dtype=torch.bfloat16: torch.randn(*s, device=dev, generator=g).to(dtype)
+    B, L, d_inner, conv_dim, H, P, N = 16, 4096, 4096, 4352, 64, 64, 128
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    out = []
+
+    # a3 causal_conv1d_fn: channel-last view of zxbcdt's xBC slice (row pitch 8512), SiLU
+    zx = rn(B, L, 8512)
+    xBC = zx[..., d_inner:d_inner + conv_dim].transpose(1, 2)
+    w, b = rn(conv_dim, 4, dtype=torch.float32), rn(conv_dim, dtype=torch.float32)
+    t = timeit(lambda: causal_conv1d_fn(xBC, w, b, activation="silu"))
+    by = 2 * B * L * conv_dim * 2
+    out.append(dict(op="causal_conv1d_fn fwd (B=16, L=4096, D=4352, channel-last slice, silu)", ms=t * 1e3, bytes=by))
+
+    # a5 gated RMSNorm (norm_before_gate=False), rows of 4096
+    y, z, nw = rn(B * L, d_inner), rn(B * L, d_inner), torch.ones(d_inner, device=dev)
+    t = timeit(lambda: rmsnorm_fn(y, nw, None, z=z, eps=1e-5, group_size=d_inner, norm_before_gate=False))
+    by = 3 * B * L * d_inner * 2
+    out.append(dict(op="rmsnorm_fn gated fwd (65536 rows x 4096)", ms=t * 1e3, bytes=by))
+
+    # f1 fused residual add + RMSNorm (block.py:86-95): x bf16 + residual fp32 -> y bf16 + residual fp32
+    xh, res, w2 = rn(B * L // 4, 2048), rn(B * L // 4, 2048, dtype=torch.float32), torch.ones(2048, device=dev)
+    t = timeit(lambda: layer_norm_fn(xh, w2, None, residual=res, prenorm=True, residual_in_fp32=True, eps=1e-5, is_rms_norm=True))
+    by = (B * L // 4) * 2048 * (2 + 4 + 2 + 4)
+    out.append(dict(op="layer_norm_fn add+rmsnorm prenorm fwd (16384 rows x 2048)", ms=t * 1e3, bytes=by))
+
+    # a8 selective_state_update, batch 64, fp32 state, stride-0 broadcast operands exactly as Mamba2.step passes them
+    Bd = 64
+    state = rn(Bd, H, P, N, dtype=torch.float32)
+    xs, dts = rn(Bd, H, P), rn(Bd, H)[:, :, None].expand(Bd, H, P)
+    A = (-torch.rand(H, device=dev, generator=g) * 15 - 1)[:, None, None].expand(H, P, N)
+    Bs, Cs = rn(Bd, 1, N), rn(Bd, 1, N)
+    D = torch.ones(H, device=dev)[:, None].expand(H, P)
+    dtb = torch.zeros(H, device=dev)[:, None].expand(H, P)
+    t = timeit(lambda: selective_state_update(state, xs, dts, A, Bs, Cs, D, z=None, dt_bias=dtb, dt_softplus=True), flush=flush)
+    by = 2 * Bd * H * P * N * 4 + 2 * (2 * Bd * H * P + Bd * H + 2 * Bd * N)
+    out.append(dict(op="selective_state_update (B=64, fp32 state, L2 flushed)", ms=t * 1e3, bytes=by))
+    state16 = state.bfloat16()
+    t = timeit(lambda: selective_state_update(state16, xs, dts, A, Bs, Cs, D, z=None, dt_bias=dtb, dt_softplus=True), flush=flush)
+    by = 2 * Bd * H * P * N * 2 + 2 * (2 * Bd * H * P + Bd * H + 2 * Bd * N)
+    out.append(dict(op="selective_state_update (B=64, bf16 state, L2 flushed)", ms=t * 1e3, bytes=by))
+
+    # a7 causal_conv1d_update, batch 64
+    cs, xu = rn(Bd, conv_dim, 4), rn(Bd, conv_dim)
+    t = timeit(lambda: causal_conv1d_update(xu, cs, w, b, "silu"), flush=flush)
+    by = Bd * conv_dim * (2 * 4 * 2 + 2 * 2)
+    out.append(dict(op="causal_conv1d_update (B=64, D=4352, L2 flushed)", ms=t * 1e3, bytes=by))
+
+    for o in out:
+        o["achieved_gbs"] = o["bytes"] / (o["ms"] / 1e3) / 1e9
+        o["peak_gbs"] = hbm
+        o["frac"] = o["achieved_gbs"] / hbm
+        print(json.dumps(o), flush=True)
+
+
+if __name__ == "__main__":
+    main()
