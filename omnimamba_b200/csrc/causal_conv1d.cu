@@ -60,7 +60,7 @@ __device__ __forceinline__ void load_tok(const ConvArgs& a, int b, int d0, int t
   }
 }
 
-template <typename T, int VEC, int W>
+template <typename T, int VEC, int W, bool SEQ>
 __global__ void __launch_bounds__(32 * kSegs) conv1d_fwd_kernel(ConvArgs a) {
   const int d0 = (blockIdx.x * 32 + threadIdx.x) * VEC;
   const int b = blockIdx.z;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(32 * kSegs) conv1d_fwd_kernel(ConvArgs a) {
   for (int k = 0; k < W - 1; ++k) {
     load_tok<T, VEC, W>(a, b, d0, t0 - (W - 1) + k, win[k + 1]);
     const int tt = t0 - (W - 1) + k;
-    sid[k + 1] = (a.seq_idx && tt >= 0) ? a.seq_idx[b * a.ss_b + tt * a.ss_l] : 0;
+    sid[k + 1] = (SEQ && tt >= 0) ? a.seq_idx[b * a.ss_b + tt * a.ss_l] : 0;
   }
   const int tend = min(t0 + kTL, a.L);
   const T* xp = static_cast<const T*>(a.x) + b * a.xs_b + d0 * a.xs_d;
@@ -107,21 +107,114 @@ __global__ void __launch_bounds__(32 * kSegs) conv1d_fwd_kernel(ConvArgs a) {
       sid[k] = sid[k + 1];
     }
     ldv<T, VEC>(xp + t * a.xs_l, win[W - 1]);
-    sid[W - 1] = a.seq_idx ? a.seq_idx[b * a.ss_b + t * a.ss_l] : 0;
+    sid[W - 1] = SEQ ? a.seq_idx[b * a.ss_b + t * a.ss_l] : 0;
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = bia[v];
 #pragma unroll
     for (int k = 0; k < W; ++k) {
-      const bool same = (sid[k] == sid[W - 1]);
+      if constexpr (SEQ) {
+        const bool same = (sid[k] == sid[W - 1]);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] += same ? wgt[k][v] * win[k][v] : 0.f;
+        for (int v = 0; v < VEC; ++v) acc[v] += same ? wgt[k][v] * win[k][v] : 0.f;
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wgt[k][v], win[k][v], acc[v]);
+      }
     }
     if (a.silu) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = silu_f(acc[v]);
     }
     stv<T, VEC>(op + t * a.os_l, acc);
+  }
+}
+
+// ---- fast path of the forward: 16-bit channel-last I/O, width 4, no seq_idx / initial / final states ------------------
+// (the call Mamba2.forward makes on the training and prefill paths).  The generic kernel above needs 104 registers at 8
+// channels per thread, which limits it to 16 warps per SM and leaves it latency-bound (ncu: 23 % occupancy, 10 warps stalled
+// on loads per issue).  Here a thread owns 4 channels (8-byte vectors; a warp still covers 256 contiguous bytes per token),
+// walks 64 tokens with the three previous inputs in registers and issues the loads of 8 tokens before touching them.
+constexpr int kTLF = 64;
+template <typename T> __device__ __forceinline__ void unpack4(uint2 r, float (&o)[4]);
+template <> __device__ __forceinline__ void unpack4<__nv_bfloat16>(uint2 r, float (&o)[4]) {
+  o[0] = __uint_as_float(r.x << 16); o[1] = __uint_as_float(r.x & 0xffff0000u);
+  o[2] = __uint_as_float(r.y << 16); o[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack4<__half>(uint2 r, float (&o)[4]) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ uint2 pack4(const float (&o)[4]);
+template <> __device__ __forceinline__ uint2 pack4<__nv_bfloat16>(const float (&o)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+template <> __device__ __forceinline__ uint2 pack4<__half>(const float (&o)[4]) {
+  const __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(32 * kSegs, 8) conv1d_fwd_fast_kernel(ConvArgs a) {
+  const int d0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int b = blockIdx.z;
+  const int t0 = (blockIdx.y * kSegs + threadIdx.y) * kTLF;
+  if (d0 >= a.D || t0 >= a.L) return;
+  float w[4][4], bia[4];  // w[k][v]: tap k (k = 3 multiplies the current token) of channel d0 + v
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k][v] = ld_any(a.w, a.w_dtype, (d0 + v) * a.ws_d + k * a.ws_w);
+    bia[v] = a.bias ? ld_any(a.bias, a.b_dtype, (d0 + v) * a.bs_d) : 0.f;
+  }
+  const T* xp = static_cast<const T*>(a.x) + b * a.xs_b + d0 + (int64_t)t0 * a.xs_l;
+  T* op = static_cast<T*>(a.out) + b * a.os_b + d0 + (int64_t)t0 * a.os_l;
+  float p1[4], p2[4], p3[4];  // x[t-1], x[t-2], x[t-3]
+  {
+    const uint2 z2 = make_uint2(0u, 0u);
+    unpack4<T>(t0 >= 1 ? __ldg(reinterpret_cast<const uint2*>(xp - a.xs_l)) : z2, p1);
+    unpack4<T>(t0 >= 2 ? __ldg(reinterpret_cast<const uint2*>(xp - 2 * a.xs_l)) : z2, p2);
+    unpack4<T>(t0 >= 3 ? __ldg(reinterpret_cast<const uint2*>(xp - 3 * a.xs_l)) : z2, p3);
+  }
+  auto token = [&](uint2 raw, T* dst) {
+    float c[4], acc[4];
+    unpack4<T>(raw, c);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      acc[v] = fmaf(w[3][v], c[v], fmaf(w[2][v], p1[v], fmaf(w[1][v], p2[v], fmaf(w[0][v], p3[v], bia[v]))));
+      if (SILU) acc[v] = silu_f(acc[v]);
+      p3[v] = p2[v]; p2[v] = p1[v]; p1[v] = c[v];
+    }
+    *reinterpret_cast<uint2*>(dst) = pack4<T>(acc);
+  };
+  const int n = min(kTLF, a.L - t0);
+  int i = 0;
+#pragma unroll 1
+  for (; i + 8 <= n; i += 8) {
+    uint2 raw[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) raw[u] = __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(i + u) * a.xs_l));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) token(raw[u], op + (int64_t)(i + u) * a.os_l);
+  }
+  for (; i < n; ++i) token(__ldg(reinterpret_cast<const uint2*>(xp + (int64_t)i * a.xs_l)), op + (int64_t)i * a.os_l);
+}
+
+template <typename T>
+bool try_launch_fwd_fast(const ConvArgs& a, int W, const omni_tensor_t& x, const omni_tensor_t& o, cudaStream_t s) {
+  if constexpr (sizeof(T) != 2) return false;
+  else {
+    if (W != 4 || a.seq_idx || a.init || a.fin || a.xs_d != 1 || a.os_d != 1 || a.D % 4 != 0 || a.L == 0) return false;
+    auto ok8 = [](const omni_tensor_t& t) {  // 8-byte vectors along the channel dim
+      return reinterpret_cast<uintptr_t>(t.data) % 8 == 0 && (t.shape[0] <= 1 || t.stride[0] % 4 == 0) &&
+             (t.shape[2] <= 1 || t.stride[2] % 4 == 0);
+    };
+    if (!ok8(x) || !ok8(o)) return false;
+    dim3 block(32, kSegs), grid((a.D + 127) / 128, (a.L + kSegs * kTLF - 1) / (kSegs * kTLF), a.B);
+    if (a.silu) conv1d_fwd_fast_kernel<T, true><<<grid, block, 0, s>>>(a);
+    else conv1d_fwd_fast_kernel<T, false><<<grid, block, 0, s>>>(a);
+    return true;
   }
 }
 
@@ -348,9 +441,18 @@ int launch_fwd_w(const ConvArgs& a, int W, cudaStream_t s) {
   dim3 block(32, kSegs), grid((a.D + 32 * VEC - 1) / (32 * VEC), (a.L + kSegs * kTL - 1) / (kSegs * kTL), a.B);
   if (grid.y == 0) grid.y = 1;
   switch (W) {
-    case 2: conv1d_fwd_kernel<T, VEC, 2><<<grid, block, 0, s>>>(a); break;
-    case 3: conv1d_fwd_kernel<T, VEC, 3><<<grid, block, 0, s>>>(a); break;
-    default: conv1d_fwd_kernel<T, VEC, 4><<<grid, block, 0, s>>>(a); break;
+    case 2:
+      if (a.seq_idx) conv1d_fwd_kernel<T, VEC, 2, true><<<grid, block, 0, s>>>(a);
+      else conv1d_fwd_kernel<T, VEC, 2, false><<<grid, block, 0, s>>>(a);
+      break;
+    case 3:
+      if (a.seq_idx) conv1d_fwd_kernel<T, VEC, 3, true><<<grid, block, 0, s>>>(a);
+      else conv1d_fwd_kernel<T, VEC, 3, false><<<grid, block, 0, s>>>(a);
+      break;
+    default:
+      if (a.seq_idx) conv1d_fwd_kernel<T, VEC, 4, true><<<grid, block, 0, s>>>(a);
+      else conv1d_fwd_kernel<T, VEC, 4, false><<<grid, block, 0, s>>>(a);
+      break;
   }
   OMNI_CUDA_LAUNCH_CHECK("conv1d_fwd_kernel");
   return OMNI_OK;
@@ -427,6 +529,10 @@ extern "C" int omni_causal_conv1d_fwd(const omni_conv1d_fwd_params_t* p, void* s
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return OMNI_DISPATCH_FLOAT(x.dtype, T, [&]() -> int {
     constexpr int V = 16 / sizeof(T);
+    if (try_launch_fwd_fast<T>(a, W, x, o, s)) {
+      OMNI_CUDA_LAUNCH_CHECK("conv1d_fwd_fast_kernel");
+      return OMNI_OK;
+    }
     if (vec_ok(x, V) && vec_ok(o, V)) return launch_fwd_w<T, V>(a, W, s);
     return launch_fwd_w<T, 1>(a, W, s);
   });

@@ -9,6 +9,8 @@
 // input/output element crosses HBM once.  Loads/stores are 16-byte vectors when shapes allow.
 // The backward kernels are persistent over rows and keep dweight/dbias partial sums in registers; they
 // write one fp32 partial row per CTA (deterministic, no atomics) that the caller sums.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace omni {
@@ -130,6 +132,94 @@ __global__ void __launch_bounds__(kThreads) norm_gated_fwd_kernel(GatedArgs a) {
         y[k] = v;
       }
       st8<VEC>(a.out.p, a.out.dtype, row * a.out.rs + c0 + col, valid, y);
+    }
+  }
+}
+
+// ---- fast path of the gated RMSNorm forward (Mamba2.norm as OmniMamba configures it) -------------------------------
+// y = rmsnorm(x * silu(z)) * w, one group, x / z / out in the same 16-bit type, D = NCH * 2048.  The generic kernel above
+// executes ~35 instructions per element (runtime dtype dispatch, mean / bias / gate-order generality) and one CTA per row;
+// here a persistent CTA keeps its weight columns in registers, loads the next row while the current one is reduced and
+// uses one __syncthreads per row (the cross-warp scratch is double-buffered).
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& r, float (&o)[8]);
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& r, float (&o)[8]) {
+  o[0] = __uint_as_float(r.x << 16); o[1] = __uint_as_float(r.x & 0xffff0000u);
+  o[2] = __uint_as_float(r.y << 16); o[3] = __uint_as_float(r.y & 0xffff0000u);
+  o[4] = __uint_as_float(r.z << 16); o[5] = __uint_as_float(r.z & 0xffff0000u);
+  o[6] = __uint_as_float(r.w << 16); o[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack8<__half>(const uint4& r, float (&o)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    o[2 * i] = f.x; o[2 * i + 1] = f.y;
+  }
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(kThreads, 4) rms_gated_fast_kernel(GatedArgs a) {
+  __shared__ float red[2][kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float w[NCH][8];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) ld8<true>(a.w, a.w_dtype, (i * kThreads + tid) * 8, 8, w[i]);
+  const T* xb = static_cast<const T*>(a.x.p);
+  const T* zb = static_cast<const T*>(a.z.p);
+  T* ob = static_cast<T*>(a.out.p);
+  uint4 rx[NCH], rz[NCH];
+  auto load = [&](int64_t r) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      rx[i] = __ldg(reinterpret_cast<const uint4*>(xb + r * a.x.rs + (i * kThreads + tid) * 8));
+      rz[i] = __ldg(reinterpret_cast<const uint4*>(zb + r * a.z.rs + (i * kThreads + tid) * 8));
+    }
+  };
+  int64_t row = blockIdx.x;
+  if (row < a.M) load(row);
+  const float inv_d = 1.f / (float)a.D;
+#pragma unroll 1
+  for (int it = 0; row < a.M; row += gridDim.x, ++it) {
+    float u[NCH][8];
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      float xv[8], zv[8];
+      unpack8<T>(rx[i], xv);
+      unpack8<T>(rz[i], zv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        u[i][k] = xv[k] * silu_f(zv[k]);
+        s2 = fmaf(u[i][k], u[i][k], s2);
+      }
+    }
+    const int64_t nrow = row + gridDim.x;
+    if (nrow < a.M) load(nrow);  // next row in flight during the reduction and the stores
+    s2 = warp_sum(s2);
+    if (lane == 0) red[it & 1][warp] = s2;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) tot += red[it & 1][k];
+    const float rstd = rsqrtf(tot * inv_d + a.eps);
+    if (tid == 0 && a.rstd) a.rstd[row] = rstd;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      uint4 o;
+      o.x = pack2<T>(u[i][0] * rstd * w[i][0], u[i][1] * rstd * w[i][1]);
+      o.y = pack2<T>(u[i][2] * rstd * w[i][2], u[i][3] * rstd * w[i][3]);
+      o.z = pack2<T>(u[i][4] * rstd * w[i][4], u[i][5] * rstd * w[i][5]);
+      o.w = pack2<T>(u[i][6] * rstd * w[i][6], u[i][7] * rstd * w[i][7]);
+      *reinterpret_cast<uint4*>(ob + row * a.out.rs + (i * kThreads + tid) * 8) = o;
     }
   }
 }
@@ -439,6 +529,21 @@ extern "C" int omni_norm_gated_fwd(const omni_norm_gated_fwd_params_t* p, void* 
   dim3 grid((unsigned)M, (unsigned)ng);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nch = (int)(((gs) + kThreads * 8 - 1) / (kThreads * 8));
+  // fast path: gate-then-RMSNorm, one group of NCH * 2048 columns, 16-bit x / z / out of one type, no bias
+  if (vec && a.is_rms && present(p->z) && !a.norm_before_gate && ng == 1 && !present(p->bias) && !present(p->mean) &&
+      (D == 2048 || D == 4096 || D == 8192) && p->x.dtype != OMNI_F32 && p->z.dtype == p->x.dtype && p->out.dtype == p->x.dtype) {
+    const unsigned gridp = (unsigned)std::min<int64_t>(M, (int64_t)sm_count() * 4);  // 4 resident CTAs per SM (64 registers)
+#define OMNI_LAUNCH_FAST(T)                                                               \
+    do {                                                                                  \
+      if (D == 2048) rms_gated_fast_kernel<T, 1><<<gridp, kThreads, 0, s>>>(a);           \
+      else if (D == 4096) rms_gated_fast_kernel<T, 2><<<gridp, kThreads, 0, s>>>(a);      \
+      else rms_gated_fast_kernel<T, 4><<<gridp, kThreads, 0, s>>>(a);                     \
+    } while (0)
+    if (p->x.dtype == OMNI_BF16) OMNI_LAUNCH_FAST(__nv_bfloat16); else OMNI_LAUNCH_FAST(__half);
+#undef OMNI_LAUNCH_FAST
+    OMNI_CUDA_LAUNCH_CHECK("rms_gated_fast_kernel");
+    return OMNI_OK;
+  }
 #define OMNI_LAUNCH_NCH(V, N) norm_gated_fwd_kernel<V, N><<<grid, kThreads, 0, s>>>(a)
   if (vec) { if (nch <= 1) OMNI_LAUNCH_NCH(true, 1); else if (nch == 2) OMNI_LAUNCH_NCH(true, 2); else OMNI_LAUNCH_NCH(true, 4); }
   else { if (nch <= 1) OMNI_LAUNCH_NCH(false, 1); else if (nch == 2) OMNI_LAUNCH_NCH(false, 2); else OMNI_LAUNCH_NCH(false, 4); }

@@ -17,7 +17,9 @@
 namespace omni {
 namespace {
 
-constexpr int kRows = 4;
+// rows (p) per warp: enough 16-byte loads in flight per lane to cover the HBM latency (8 x 512 B fp32 rows, 16 x 256 B
+// 16-bit rows = 4 KB per warp)
+template <typename TS> constexpr int rows_of() { return 4; }  // (8 / 16 rows per warp measured slower: fewer warps in flight)
 constexpr int kWarps = 4;
 
 struct SsuArgs {
@@ -70,6 +72,7 @@ template <> __device__ __forceinline__ void st4<__half>(__half* p, const float (
 // NV = number of 4-element vectors per lane (N = 128 * NV, or N <= 128 with idle lanes when NV == 1).
 template <typename TS, int NV, bool TIE_A>
 __global__ void __launch_bounds__(32 * kWarps) ssu_kernel(SsuArgs a) {
+  constexpr int kRows = rows_of<TS>() / NV;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pblocks = (a.P + kRows - 1) / kRows;
   const int64_t task = (int64_t)blockIdx.x * kWarps + warp;
@@ -152,10 +155,12 @@ __global__ void __launch_bounds__(32 * kWarps) ssu_kernel(SsuArgs a) {
 
 template <typename TS>
 int launch(const SsuArgs& a, cudaStream_t s) {
-  const int pblocks = (a.P + kRows - 1) / kRows;
+  const bool tie = a.A_n == 0;
+  const int nv = a.N <= 128 ? 1 : 2;
+  const int krows = rows_of<TS>() / nv;
+  const int pblocks = (a.P + krows - 1) / krows;
   const int64_t tasks = (int64_t)a.B * a.H * pblocks;
   const unsigned grid = (unsigned)((tasks + kWarps - 1) / kWarps);
-  const bool tie = a.A_n == 0;
   if (a.N <= 128) {
     if (tie) ssu_kernel<TS, 1, true><<<grid, 32 * kWarps, 0, s>>>(a);
     else ssu_kernel<TS, 1, false><<<grid, 32 * kWarps, 0, s>>>(a);

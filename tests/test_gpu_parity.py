@@ -59,6 +59,21 @@ def test_conv1d_fwd(ops, dtype, channel_last, B, D, L, W, act):
     assert out.stride() == x.stride() or not channel_last
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("L", [1, 7, 64, 65, 329, 1024])
+def test_conv1d_fwd_fast_path_zxbcdt_slice(ops, dtype, L):
+    """The call Mamba2.forward makes at d_model=2048: xBC = zxbcdt[..., 4096:8448].transpose(1, 2) (row pitch 8512), width 4,
+    SiLU - the 4-channel-per-thread fast kernel, segment boundaries (64 tokens per thread) and ragged tails included."""
+    g = torch.Generator().manual_seed(L)
+    zx = torch.randn(2, L, 8512, generator=g).to(dtype)
+    x = zx[..., 4096:4096 + 4352].transpose(1, 2)
+    w, b = torch.randn(4352, 4, generator=g) / 2, torch.randn(4352, generator=g)
+    ref = oracle.causal_conv1d_ref(x, w, b, activation="silu", compute_dtype=torch.float32)
+    xd = zx.to(DEV)[..., 4096:4096 + 4352].transpose(1, 2)
+    out = ops.causal_conv1d_fn(xd, w.to(DEV), b.to(DEV), activation="silu")
+    check(out, ref, TOL[dtype], "conv fast out")
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv1d_states(ops, dtype):
     g = torch.Generator().manual_seed(5)
@@ -261,6 +276,21 @@ def test_norm_gated(ops, dtype, M, Dm, gs, nbg, gated):
     check(wg.grad, wr.grad, GTOL[dtype], "gated norm dw")
     if gated:
         check(zg.grad, zr.grad, TOL[dtype] * 10, "gated norm dz")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,Dm", [(1, 2048), (333, 4096), (1500, 4096), (40, 8192)])
+def test_norm_gated_fast_path(ops, dtype, M, Dm):
+    """rmsnorm(x * silu(z)) * w with one group of 2048 / 4096 / 8192 columns in a 16-bit type: the persistent fast kernel
+    (more rows than resident CTAs at M=1500, fewer at M=1), strided x rows (y is a (B*L, H*P) view of the scan output)."""
+    g = torch.Generator().manual_seed(M + Dm)
+    xfull = torch.randn(M, Dm + 64, generator=g).to(dtype)
+    x, z = xfull[:, :Dm], torch.randn(M, Dm, generator=g).to(dtype)
+    w = torch.rand(Dm, generator=g) + 0.5
+    ref = oracle.rmsnorm_gated_ref(x, w, None, z=z, eps=1e-5, group_size=Dm, norm_before_gate=False)
+    with torch.no_grad():
+        out = ops.rmsnorm_fn(xfull.to(DEV)[:, :Dm], w.to(DEV), None, z=z.to(DEV), eps=1e-5, group_size=Dm, norm_before_gate=False)
+    check(out, ref, TOL[dtype], "gated norm fast out")
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
