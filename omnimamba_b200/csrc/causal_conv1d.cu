@@ -377,6 +377,140 @@ __global__ void __launch_bounds__(32 * kSegs) conv1d_bwd_kernel(ConvArgs a) {
   }
 }
 
+// ---- fast path of the backward: same configuration as conv1d_fwd_fast_kernel ------------------------------------------
+// A thread owns 4 channels and `tl` consecutive tokens.  It walks t = t0 .. t0 + tl + 2 keeping the last four inputs and the
+// last four dc = dout * act'(c) in registers: c[t] is recomputed from the window, dweight / dbias accumulate over the
+// thread's own tokens, dx[t-3] = sum_k w[k] dc[t-k] leaves as soon as its four dc are known (the three tokens past the
+// thread's range are re-read: L2 hits).  Loads of 8 tokens (x and dout) are issued before any of them is used.
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(32 * kSegs, 4) conv1d_bwd_fast_kernel(ConvArgs a, int tl) {
+  __shared__ float red[kSegs][32][21];
+  const int d0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int b = blockIdx.z;
+  const int t0 = (blockIdx.y * kSegs + threadIdx.y) * tl;
+  const bool active = d0 < a.D && t0 < a.L;
+  float dwa[4][4], dba[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    dba[v] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dwa[k][v] = 0.f;
+  }
+  if (active) {
+    float w[4][4], bia[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k][v] = ld_any(a.w, a.w_dtype, (d0 + v) * a.ws_d + k * a.ws_w);
+      bia[v] = a.bias ? ld_any(a.bias, a.b_dtype, (d0 + v) * a.bs_d) : 0.f;
+    }
+    const T* xp = static_cast<const T*>(a.x) + b * a.xs_b + d0;
+    const T* gp = static_cast<const T*>(a.dout) + b * a.gs_b + d0;
+    T* dxp = static_cast<T*>(a.dx) + b * a.ds_b + d0;
+    const uint2 z2 = make_uint2(0u, 0u);
+    float p1[4], p2[4], p3[4];     // x[t-1], x[t-2], x[t-3]
+    float g1[4], g2[4], g3[4];     // dc[t-1], dc[t-2], dc[t-3]
+    unpack4<T>(t0 >= 1 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 1) * a.xs_l)) : z2, p1);
+    unpack4<T>(t0 >= 2 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 2) * a.xs_l)) : z2, p2);
+    unpack4<T>(t0 >= 3 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 3) * a.xs_l)) : z2, p3);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) g1[v] = g2[v] = g3[v] = 0.f;
+    const int own_end = min(t0 + tl, a.L);
+    const int tlast = own_end + 3;   // exclusive; dc beyond L is zero
+    auto token = [&](int t, uint2 rx, uint2 rg) {
+      float c[4], g[4];
+      unpack4<T>(rx, c);
+      unpack4<T>(rg, g);
+      const bool own = t < own_end;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (SILU) {
+          const float pre = fmaf(w[3][v], c[v], fmaf(w[2][v], p1[v], fmaf(w[1][v], p2[v], fmaf(w[0][v], p3[v], bia[v]))));
+          g[v] *= dsilu_f(pre);
+        }
+        if (own) {
+          dba[v] += g[v];
+          dwa[3][v] = fmaf(g[v], c[v], dwa[3][v]);
+          dwa[2][v] = fmaf(g[v], p1[v], dwa[2][v]);
+          dwa[1][v] = fmaf(g[v], p2[v], dwa[1][v]);
+          dwa[0][v] = fmaf(g[v], p3[v], dwa[0][v]);
+        }
+      }
+      const int sidx = t - 3;
+      if (sidx >= t0) {  // (sidx < own_end always holds: t < own_end + 3)
+        float r[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) r[v] = fmaf(w[0][v], g[v], fmaf(w[1][v], g1[v], fmaf(w[2][v], g2[v], w[3][v] * g3[v])));
+        *reinterpret_cast<uint2*>(dxp + (int64_t)sidx * a.ds_l) = pack4<T>(r);
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        p3[v] = p2[v]; p2[v] = p1[v]; p1[v] = c[v];
+        g3[v] = g2[v]; g2[v] = g1[v]; g1[v] = g[v];
+      }
+    };
+    int t = t0;
+#pragma unroll 1
+    for (; t + 8 <= min(tlast, a.L); t += 8) {
+      uint2 rx[8], rg[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        rx[u] = __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t + u) * a.xs_l));
+        rg[u] = __ldg(reinterpret_cast<const uint2*>(gp + (int64_t)(t + u) * a.gs_l));
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) token(t + u, rx[u], rg[u]);
+    }
+    for (; t < tlast; ++t) {
+      const bool in = t < a.L;
+      token(t, in ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)t * a.xs_l)) : z2,
+            in ? __ldg(reinterpret_cast<const uint2*>(gp + (int64_t)t * a.gs_l)) : z2);
+    }
+  }
+  // reduce dweight / dbias over the block's token segments, then one atomic per (channel, tap)
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[threadIdx.y][threadIdx.x][v * 5 + k] = dwa[k][v];
+    red[threadIdx.y][threadIdx.x][v * 5 + 4] = dba[v];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && d0 < a.D) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+#pragma unroll
+      for (int k = 0; k <= 4; ++k) {
+        float sum = 0.f;
+#pragma unroll
+        for (int gsg = 0; gsg < kSegs; ++gsg) sum += red[gsg][threadIdx.x][v * 5 + k];
+        if (k < 4) atomicAdd(a.dw + (int64_t)(d0 + v) * 4 + k, sum);
+        else if (a.db) atomicAdd(a.db + d0 + v, sum);
+      }
+    }
+  }
+}
+
+template <typename T>
+bool try_launch_bwd_fast(const ConvArgs& a, int W, const omni_tensor_t& x, const omni_tensor_t& g, const omni_tensor_t& dx,
+                         cudaStream_t s) {
+  if constexpr (sizeof(T) != 2) return false;
+  else {
+    if (W != 4 || a.seq_idx || a.init || a.dinit || a.xs_d != 1 || a.gs_d != 1 || a.ds_d != 1 || a.D % 4 != 0) return false;
+    auto ok8 = [](const omni_tensor_t& t) {
+      return reinterpret_cast<uintptr_t>(t.data) % 8 == 0 && (t.shape[0] <= 1 || t.stride[0] % 4 == 0) &&
+             (t.shape[2] <= 1 || t.stride[2] % 4 == 0);
+    };
+    if (!ok8(x) || !ok8(g) || !ok8(dx)) return false;
+    // tokens per thread: 256 when there is enough work to fill the GPU with it (4x fewer partial-sum atomics), else 64
+    const int64_t cols = (a.D + 127) / 128;
+    const int tl = cols * a.B * ((a.L + kSegs * 256 - 1) / (kSegs * 256)) >= 4 * (int64_t)sm_count() ? 256 : 64;
+    dim3 block(32, kSegs), grid((unsigned)cols, (a.L + kSegs * tl - 1) / (kSegs * tl), a.B);
+    if (a.silu) conv1d_bwd_fast_kernel<T, true><<<grid, block, 0, s>>>(a, tl);
+    else conv1d_bwd_fast_kernel<T, false><<<grid, block, 0, s>>>(a, tl);
+    return true;
+  }
+}
+
 struct UpdArgs {
   const void* x; void* st; const void* w; const void* bias; const int* cs; void* out;
   int64_t xs_b, xs_d, xs_t, ss_b, ss_d, ss_s, os_b, os_d, os_t, ws_d, ws_w, bs_d;
@@ -584,6 +718,10 @@ extern "C" int omni_causal_conv1d_bwd(const omni_conv1d_bwd_params_t* p, void* s
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return OMNI_DISPATCH_FLOAT(x.dtype, T, [&]() -> int {
     constexpr int V = 16 / sizeof(T);
+    if (try_launch_bwd_fast<T>(a, W, x, g, dx, s)) {
+      OMNI_CUDA_LAUNCH_CHECK("conv1d_bwd_fast_kernel");
+      return OMNI_OK;
+    }
     if (vec_ok(x, V) && vec_ok(g, V) && vec_ok(dx, V)) return launch_bwd_w<T, V>(a, W, s);
     return launch_bwd_w<T, 1>(a, W, s);
   });

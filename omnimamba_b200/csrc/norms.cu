@@ -315,6 +315,80 @@ __global__ void __launch_bounds__(kThreads) norm_gated_bwd_kernel(GatedArgs a) {
   }
 }
 
+// ---- fast path of the gated RMSNorm backward (same configuration as rms_gated_fast_kernel) ---------------------------
+// One thread owns 8 columns of the row (blockDim = D / 8), so the weight and the dweight partial sums of its columns stay in
+// 16 registers for the whole launch; per row it keeps the raw 16-bit x / z / dy vectors, reduces c1 = mean(xhat * w dy)
+// across the CTA with one __syncthreads (double-buffered scratch) while the next row's vectors are already in flight, and
+// recomputes the cheap per-element terms after the reduction instead of holding them in registers.
+template <typename T, bool YREC>
+__global__ void __launch_bounds__(1024, 1) rms_gated_bwd_fast_kernel(GatedArgs a) {
+  __shared__ float red[2][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int col = tid * 8;
+  float w[8], dwa[8];
+  ld8<true>(a.w, a.w_dtype, col, 8, w);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dwa[k] = 0.f;
+  const T* xb = static_cast<const T*>(a.x.p);
+  const T* zb = static_cast<const T*>(a.z.p);
+  const T* gb = static_cast<const T*>(a.dout.p);
+  uint4 rx, rz, rg;
+  float rstd_n = 0.f;
+  auto load = [&](int64_t r) {
+    rx = __ldg(reinterpret_cast<const uint4*>(xb + r * a.x.rs + col));
+    rz = __ldg(reinterpret_cast<const uint4*>(zb + r * a.z.rs + col));
+    rg = __ldg(reinterpret_cast<const uint4*>(gb + r * a.dout.rs + col));
+    rstd_n = __ldg(a.rstd + r);
+  };
+  int64_t row = blockIdx.x;
+  if (row < a.M) load(row);
+  const float inv_d = 1.f / (float)a.D;
+#pragma unroll 1
+  for (int it = 0; row < a.M; row += gridDim.x, ++it) {
+    float gv[8], xh[8], sa[8], sb[8];  // w dy, xhat, silu(z), x dsilu(z)
+    const float rstd = rstd_n;
+    float c1 = 0.f;
+    {
+      float xv[8], zv[8];
+      unpack8<T>(rx, xv);
+      unpack8<T>(rz, zv);
+      unpack8<T>(rg, gv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float sg = sigmoid_f(zv[k]);
+        sa[k] = zv[k] * sg;
+        sb[k] = xv[k] * (sg + sa[k] * (1.f - sg));    // x * d silu / dz,  d silu / dz = sg + silu (1 - sg)
+        xh[k] = xv[k] * sa[k] * rstd;                 // xhat = x silu(z) rstd
+        dwa[k] = fmaf(gv[k], xh[k], dwa[k]);
+        gv[k] *= w[k];                                // w dy
+        c1 = fmaf(xh[k], gv[k], c1);
+      }
+    }
+    const int64_t nrow = row + gridDim.x;
+    if (nrow < a.M) load(nrow);  // (the raw vectors of this row are fully unpacked above)
+    c1 = warp_sum(c1);
+    if (lane == 0) red[it & 1][warp] = c1;
+    __syncthreads();
+    float tot = 0.f;
+    for (int k = 0; k < nwarps; ++k) tot += red[it & 1][k];
+    c1 = tot * inv_d;
+    uint32_t odx[4], odz[4], oy[4];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const float du0 = (gv[k] - xh[k] * c1) * rstd, du1 = (gv[k + 1] - xh[k + 1] * c1) * rstd;
+      odx[k >> 1] = pack2<T>(du0 * sa[k], du1 * sa[k + 1]);
+      odz[k >> 1] = pack2<T>(du0 * sb[k], du1 * sb[k + 1]);
+      oy[k >> 1] = pack2<T>(xh[k] * w[k], xh[k + 1] * w[k + 1]);
+    }
+    *reinterpret_cast<uint4*>(static_cast<T*>(a.dx.p) + row * a.dx.rs + col) = make_uint4(odx[0], odx[1], odx[2], odx[3]);
+    *reinterpret_cast<uint4*>(static_cast<T*>(a.dz.p) + row * a.dz.rs + col) = make_uint4(odz[0], odz[1], odz[2], odz[3]);
+    if (YREC) *reinterpret_cast<uint4*>(static_cast<T*>(a.yrec.p) + row * a.yrec.rs + col) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
+  }
+  float4* dst = reinterpret_cast<float4*>(a.dw_part + (int64_t)blockIdx.x * a.D + col);
+  dst[0] = make_float4(dwa[0], dwa[1], dwa[2], dwa[3]);
+  dst[1] = make_float4(dwa[4], dwa[5], dwa[6], dwa[7]);
+}
+
 // ---- fused add + norm ------------------------------------------------------------------------------
 struct AddNormArgs {
   T2 x, res, y, res_out, dy, dres_in, dx, dres_out;
@@ -592,6 +666,23 @@ extern "C" int omni_norm_gated_bwd(const omni_norm_gated_bwd_params_t* p, void* 
   dim3 grid((unsigned)nparts, (unsigned)ng);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nch = (int)(((gs) + kThreads * 8 - 1) / (kThreads * 8));
+  // fast path: gate-then-RMSNorm, one group of 2048 / 4096 / 8192 columns, 16-bit tensors of one type, no bias
+  if (vec && a.is_rms && present(p->z) && !a.norm_before_gate && ng == 1 && !present(p->bias) &&
+      (D == 2048 || D == 4096 || D == 8192) && p->x.dtype != OMNI_F32 && p->z.dtype == p->x.dtype &&
+      p->dout.dtype == p->x.dtype && p->dx.dtype == p->x.dtype && p->dz.dtype == p->x.dtype &&
+      (!present(p->out_recompute) || p->out_recompute.dtype == p->x.dtype)) {
+    const unsigned threads = (unsigned)(D / 8);
+    const bool yr = present(p->out_recompute);
+#define OMNI_LAUNCH_FAST(T)                                                                       \
+    do {                                                                                          \
+      if (yr) rms_gated_bwd_fast_kernel<T, true><<<(unsigned)nparts, threads, 0, s>>>(a);         \
+      else rms_gated_bwd_fast_kernel<T, false><<<(unsigned)nparts, threads, 0, s>>>(a);           \
+    } while (0)
+    if (p->x.dtype == OMNI_BF16) OMNI_LAUNCH_FAST(__nv_bfloat16); else OMNI_LAUNCH_FAST(__half);
+#undef OMNI_LAUNCH_FAST
+    OMNI_CUDA_LAUNCH_CHECK("rms_gated_bwd_fast_kernel");
+    return OMNI_OK;
+  }
 #define OMNI_LAUNCH_NCH(V, N) norm_gated_bwd_kernel<V, N><<<grid, kThreads, 0, s>>>(a)
   if (vec) { if (nch <= 1) OMNI_LAUNCH_NCH(true, 1); else if (nch == 2) OMNI_LAUNCH_NCH(true, 2); else OMNI_LAUNCH_NCH(true, 4); }
   else { if (nch <= 1) OMNI_LAUNCH_NCH(false, 1); else if (nch == 2) OMNI_LAUNCH_NCH(false, 2); else OMNI_LAUNCH_NCH(false, 4); }

@@ -64,6 +64,21 @@ def main():
     by = 3 * B * L * d_inner * 2
     out.append(dict(op="rmsnorm_fn gated fwd (65536 rows x 4096)", ms=t * 1e3, bytes=by))
 
+    # a3 / a5 backward (training path): conv1d bwd reads x, dout and writes dx; gated norm bwd reads x, z, dy and writes dx, dz
+    xg = xBC.detach().requires_grad_()
+    wg, bg = w.clone().requires_grad_(), b.clone().requires_grad_()
+    yc = causal_conv1d_fn(xg, wg, bg, activation="silu")
+    dyc = torch.randn_like(yc)
+    t = timeit(lambda: torch.autograd.grad(yc, (xg, wg, bg), dyc, retain_graph=True))
+    out.append(dict(op="causal_conv1d_fn bwd (same shape; incl. torch partial-sum reductions)", ms=t * 1e3, bytes=3 * B * L * conv_dim * 2))
+    del yc, dyc, xg
+    yg, zg, nwg = y.detach().requires_grad_(), z.detach().requires_grad_(), nw.clone().requires_grad_()
+    yn = rmsnorm_fn(yg, nwg, None, z=zg, eps=1e-5, group_size=d_inner, norm_before_gate=False)
+    dyn = torch.randn_like(yn)
+    t = timeit(lambda: torch.autograd.grad(yn, (yg, zg, nwg), dyn, retain_graph=True))
+    out.append(dict(op="rmsnorm_fn gated bwd (65536 rows x 4096; incl. torch partial-sum reduction)", ms=t * 1e3, bytes=5 * B * L * d_inner * 2))
+    del yn, dyn, yg, zg
+
     # f1 fused residual add + RMSNorm (block.py:86-95): x bf16 + residual fp32 -> y bf16 + residual fp32
     xh, res, w2 = rn(B * L // 4, 2048), rn(B * L // 4, 2048, dtype=torch.float32), torch.ones(2048, device=dev)
     t = timeit(lambda: layer_norm_fn(xh, w2, None, residual=res, prenorm=True, residual_in_fp32=True, eps=1e-5, is_rms_norm=True))

@@ -115,6 +115,31 @@ def test_conv1d_bwd(ops, dtype, channel_last, act):
     check(bg.grad, br.grad, GTOL[dtype], "conv dbias")
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,L", [(2, 1), (2, 5), (2, 64), (2, 67), (1, 329), (2, 1030), (3, 9300)])
+@pytest.mark.parametrize("act", [None, "silu"])
+def test_conv1d_bwd_fast_path_zxbcdt_slice(ops, dtype, B, L, act):
+    """Backward of the call Mamba2.forward makes at d_model=2048 (channel-last slices with row pitch 8512, width 4): the
+    4-channel-per-thread fast kernel, with 64 tokens per thread and (B=3, L=9300) 256 tokens per thread, ragged tails."""
+    if L > 2000 and (act is None or dtype == torch.float16):
+        pytest.skip("large case once")
+    g = torch.Generator().manual_seed(L + B)
+    D = 4352
+    zx = torch.randn(B, L, 8512, generator=g).to(dtype)
+    dzx = torch.randn(B, L, 8512, generator=g).to(dtype)
+    x, dy = zx[..., 4096:4096 + D].transpose(1, 2), dzx[..., 4096:4096 + D].transpose(1, 2)
+    w, b = torch.randn(D, 4, generator=g) / 2, torch.randn(D, generator=g)
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    oracle.causal_conv1d_ref(xr, wr, br, activation=act, compute_dtype=torch.float32).backward(dy)
+    zxd = zx.to(DEV).requires_grad_()
+    wg, bg = w.to(DEV).requires_grad_(), b.to(DEV).requires_grad_()
+    out = ops.causal_conv1d_fn(zxd[..., 4096:4096 + D].transpose(1, 2), wg, bg, activation=act)
+    out.backward(dzx.to(DEV)[..., 4096:4096 + D].transpose(1, 2))
+    check(zxd.grad[..., 4096:4096 + D].transpose(1, 2), xr.grad, TOL[dtype] * 4, "conv fast dx")
+    check(wg.grad, wr.grad, GTOL[dtype], "conv fast dweight")
+    check(bg.grad, br.grad, GTOL[dtype], "conv fast dbias")
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("T", [None, 3])
 def test_conv1d_update(ops, dtype, T):
@@ -287,10 +312,17 @@ def test_norm_gated_fast_path(ops, dtype, M, Dm):
     xfull = torch.randn(M, Dm + 64, generator=g).to(dtype)
     x, z = xfull[:, :Dm], torch.randn(M, Dm, generator=g).to(dtype)
     w = torch.rand(Dm, generator=g) + 0.5
-    ref = oracle.rmsnorm_gated_ref(x, w, None, z=z, eps=1e-5, group_size=Dm, norm_before_gate=False)
-    with torch.no_grad():
-        out = ops.rmsnorm_fn(xfull.to(DEV)[:, :Dm], w.to(DEV), None, z=z.to(DEV), eps=1e-5, group_size=Dm, norm_before_gate=False)
+    dy = torch.randn(M, Dm, generator=g).to(dtype)
+    xr, zr, wr = x.clone().requires_grad_(), z.clone().requires_grad_(), w.clone().requires_grad_()
+    ref = oracle.rmsnorm_gated_ref(xr, wr, None, z=zr, eps=1e-5, group_size=Dm, norm_before_gate=False)
+    ref.backward(dy)
+    xf, zg, wg = xfull.to(DEV).requires_grad_(), z.to(DEV).requires_grad_(), w.to(DEV).requires_grad_()
+    out = ops.rmsnorm_fn(xf[:, :Dm], wg, None, z=zg, eps=1e-5, group_size=Dm, norm_before_gate=False)
+    out.backward(dy.to(DEV))
     check(out, ref, TOL[dtype], "gated norm fast out")
+    check(xf.grad[:, :Dm], xr.grad, TOL[dtype] * 10, "gated norm fast dx")
+    check(zg.grad, zr.grad, TOL[dtype] * 10, "gated norm fast dz")
+    check(wg.grad, wr.grad, GTOL[dtype], "gated norm fast dw")
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
