@@ -49,6 +49,7 @@ constexpr int NS = 128;    // d_state
 // Warps that watch mbarriers for their role sit on schedulers 2 and 3 (with the TMA / MMA threads); the table warps (0, 1),
 // whose serial dt -> cumsum -> exp chain feeds every chunk, share their schedulers with no spinning warp.
 constexpr int kLeadPX = 2, kLeadE = 3;
+constexpr int kHandSlots = 128;  // hand-off slots of the half-item schedule (>= grid / 2)
 constexpr int kThreads = 512;   // 16 warps: 2 table, TMA, MMA, 8 P build + x pass, 4 epilogue + state
 
 // shared-memory map (bytes, relative to the 1024B-aligned base)
@@ -97,6 +98,8 @@ struct TcArgs {
   int dt_dtype, D_dtype, dtb_dtype, init_dtype, out_dtype;
   int dt_softplus;
   float dt_min, dt_max;
+  // half-item schedule (forward only, see the kernel): fp32 state hand-off slots [slot][128 (h,p)][128 n] and their flags
+  float* hand; int* flags;
   long long* trace; int trace_chunks;  // debug: per-event clock64 of CTA 0 (omni_debug_set_trace)
   // mode 0: the forward.  Modes 1 / 2 run only the state recurrence of the same pipeline and TMA-store the fp16 state
   // ENTERING every chunk (for the backward): 1 = forward states S_c from (x, B, sj); 2 = reverse sweep of the state
@@ -159,8 +162,9 @@ __device__ __forceinline__ float softplus_fast(float v) {
 }
 
 // Walks the chunks of this CTA's work items in processing order (one integer division per item, not per chunk).
+// A work UNIT is a contiguous range of chunk steps [c0, cend) of one item (batch, head pair): normally the whole sequence.
 struct ChunkIter {
-  int item, c, b, h0;
+  int u, c, c0, cend, b, h0;
 };
 
 // Code size matters here: sixteen warps run five different role loops, and with everything unrolled the kernel was 130 KB
@@ -227,13 +231,32 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   const int nitems = a.B * HP;
   const int nchunks = (a.L + Q - 1) / Q;
   const int hpg = a.H / a.G;                  // heads per group
-  const uint32_t my_items = blockIdx.x < (uint32_t)nitems ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const uint32_t total = my_items * nchunks;  // chunks this CTA processes; g = running chunk counter (barrier phases)
-  auto it_set = [&](ChunkIter& it, int item) {
-    it.item = item; it.c = 0; it.b = item / HP; it.h0 = (item - it.b * HP) * 2;
+  // Schedule.  CTA `bid` of `grid` takes the items bid, bid + grid, ... of the FR full rounds.  The R = nitems % grid items
+  // left over would cost every CTA a whole extra item time for R / grid of the machine (512 items on 148 SMs: 3.46 rounds
+  // run as 4).  When 2 R <= grid they are cut in two half sequences instead: CTA r < R runs the FIRST half of left-over item
+  // r before anything else and parks the fp32 state in a hand-off slot, CTA R + r runs the SECOND half after its own items -
+  // three item times later, so the flag it polls is long set - and the makespan drops from FR + 1 to FR + 1/2 item times.
+  const int grid = (int)gridDim.x, bid = (int)blockIdx.x;
+  const int FR = nitems / grid, R = nitems % grid;
+  const bool split = a.hand != nullptr && R > 0 && 2 * R <= grid && R <= kHandSlots && FR >= 1 && nchunks >= 2;
+  const int half = nchunks >> 1;
+  const int pre = (split && bid < R) ? 1 : 0;
+  const bool tail_half = split && bid >= R && bid < 2 * R, tail_full = !split && bid < R;
+  const uint32_t total = (uint32_t)(pre * half + FR * nchunks + (tail_full ? nchunks : tail_half ? nchunks - half : 0));
+  // (chunks this CTA processes; g = running chunk counter = barrier phases)
+  auto it_set = [&](ChunkIter& it, int u) {
+    int item, c0 = 0, c1 = nchunks;
+    if (pre && u == 0) { item = FR * grid + bid; c1 = half; }
+    else {
+      const int k = u - pre;
+      if (k < FR) item = k * grid + bid;
+      else if (split) { item = FR * grid + bid - R; c0 = half; }
+      else item = FR * grid + bid;
+    }
+    it.u = u; it.c = c0; it.c0 = c0; it.cend = c1; it.b = item / HP; it.h0 = (item - it.b * HP) * 2;
   };
   auto it_next = [&](ChunkIter& it) {
-    if (++it.c == nchunks) it_set(it, it.item + gridDim.x);
+    if (++it.c == it.cend) it_set(it, it.u + 1);
   };
   const int mode = a.mode;
   auto cphys = [&](int c) { return mode == 2 ? nchunks - 1 - c : c; };  // chunk visited at step c of an item
@@ -274,7 +297,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           tma_load_4d(dst + 16384, &mapX, &bars[B_SW_FULL + s3], 0, it.h0 + 1, cphys(it.c) * Q, it.b);
         };
         ChunkIter itb, itx;
-        it_set(itb, blockIdx.x);
+        it_set(itb, 0);
         itx = itb;
         for (uint32_t k = 0; k < 3 && k < total; ++k) {
           if (k < 2) { load_b(itb, k); it_next(itb); }
@@ -297,7 +320,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
       } else {
       ChunkIter it1, it2;  // chunks g + 1 and g + 2
-      it_set(it1, blockIdx.x);
+      it_set(it1, 0);
       if (mode == 0) load_c(it1);
       load_b(it1, 0); load_x(it1);
       it_next(it1);
@@ -463,7 +486,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       return __half2float(__ushort_as_half((unsigned short)bits));
     };
     ChunkIter it, itn, itp;
-    it_set(it, blockIdx.x);
+    it_set(it, 0);
     itn = it;
     load_raw(raw_a, itn, total > 0);
     it_next(itn);
@@ -479,7 +502,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const uint32_t st = g & 1, n = g >> 1;
       Tab* tab = reinterpret_cast<Tab*>(smem + SM_TAB) + st;
       if (hh == 0) TR(8);
-      if (it.c == 0) {  // new item: per-head constants
+      if (it.c == it.c0) {  // new unit: per-head constants
         Ah2 = a.A[it.h0 + hh] * 1.4426950408889634f;
         bias = a.dt_bias ? ld_any(a.dt_bias, a.dtb_dtype, it.h0 + hh) : 0.f;
       }
@@ -588,7 +611,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const uint32_t rx = (uint32_t)(i & 7) << 4;
     const uint32_t xrow = sub * 16384 + i * 128;  // byte offset of this lane's x row inside the XA / XB tiles
     ChunkIter it;
-    it_set(it, blockIdx.x);
+    it_set(it, 0);
 #pragma unroll 1
     for (uint32_t g = 0; g < total; ++g) {
       const uint32_t st = g & 1, n = g >> 1, ph = g & 1;
@@ -760,9 +783,33 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const uint32_t rx = (uint32_t)(r & 7) << 4;
     uint8_t* ybuf = smem + SM_Y + w * 4096;   // two 2 KB slots: [32 rows x 64 B] = 32 columns of one head, 64B swizzle
     ChunkIter sn, ep;  // chunk gg (state step) and chunk gg - 1 (epilogue)
-    it_set(sn, blockIdx.x);
+    it_set(sn, 0);
     ep = sn;
-    int fin_b = 0, fin_h0 = 0;  // item of the chunk whose epilogue slot ran last (owner of the state at an item boundary)
+    int pend = 0, pend_b = 0, pend_h0 = 0;  // unit that ended with the previous state step: 1 = whole item / second half, 2 = first half
+    // state at the end of a unit (all of TM_S, complete once the unit's last S-update has been waited for): the final state
+    // of the item, or - first half of a split item - the hand-off slot of this CTA followed by its flag
+    auto store_unit_state = [&]() {
+      float* dst = pend == 2 ? a.hand + ((int64_t)bid * 128 + r) * NS
+                             : (a.fin ? a.fin + ((int64_t)(pend_b * a.H + pend_h0 + hh) * HD + p) * NS : nullptr);
+      if (dst != nullptr) {
+#pragma unroll 1
+        for (int k4 = 0; k4 < 4; ++k4) {
+          uint32_t v[32];
+          tmem_ld32(tmem_addr(tb, w * 32, TM_S + 32 * k4), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(dst + 32 * k4 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                        __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
+      }
+      if (pend == 2) {
+        __threadfence();
+        named_bar_sync(1, 128);
+        if (r == 0) atomicExch(a.flags + bid, 1);
+      }
+      pend = 0;
+    };
     // iteration gg = 0 .. total: [epilogue of chunk gg - 1] then [state step of chunk gg].  The epilogue comes first: it is
     // on the chunk-to-chunk critical path (it frees the accumulators), the state step has slack until Yoff(gg).
 #pragma unroll 1
@@ -828,10 +875,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         if (w == 0) TR(22);
       }
-      if (gg > 0) {
-        fin_b = ep.b; fin_h0 = ep.h0;
-        it_next(ep);
-      }
+      if (gg > 0) it_next(ep);
       if (gg < total) {
         // ---- S16 = fp16(S) for Yoff(gg);  S <- exp(lam_last(gg)) S  (initial state on the first chunk of an item)
         const uint32_t g = gg;  // (for the trace macro)
@@ -852,20 +896,32 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         if (gg > 0) tc_fence_after();
         if (w == 0) TR(15);
-        if (sn.c == 0) {
-          if (gg > 0 && a.fin) {  // final state of the item that just ended (the item of chunk gg - 1)
-            float* dst = a.fin + ((int64_t)(fin_b * a.H + fin_h0 + hh) * HD + p) * NS;
-#pragma unroll 1
-            for (int k4 = 0; k4 < 4; ++k4) {
-              uint32_t v[32];
-              tmem_ld32(tmem_addr(tb, w * 32, TM_S + 32 * k4), v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 32; e += 4)
-                *reinterpret_cast<float4*>(dst + 32 * k4 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                                            __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        if (sn.c == sn.c0) {
+          if (pend) store_unit_state();  // the unit that just ended (its last S-update was waited for above)
+          if (sn.c0 > 0) {
+            // second half of a split item: the state after the first half comes from hand-off slot bid - R
+            const int slot = bid - R;
+            if (r == 0) {
+              int ok = 0;
+              for (int spin = 0; spin < (1 << 22) && !ok; ++spin) {  // (bounded: a scheduling bug must not hang the GPU)
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ok) : "l"(a.flags + slot) : "memory");
+                if (!ok) __nanosleep(200);
+              }
             }
-          }
+            named_bar_sync(1, 128);
+            __threadfence();
+            const float* src = a.hand + ((int64_t)slot * 128 + r) * NS;
+#pragma unroll 1
+            for (int k16 = 0; k16 < 8; ++k16) {
+              uint32_t v[16];
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 f = __ldcg(reinterpret_cast<const float4*>(src + 16 * k16 + e));
+                v[e] = __float_as_uint(f.x); v[e + 1] = __float_as_uint(f.y); v[e + 2] = __float_as_uint(f.z); v[e + 3] = __float_as_uint(f.w);
+              }
+              tmem_st16(tmem_addr(tb, w * 32, TM_S + 16 * k16), v);
+            }
+          } else {
           // state entering the item: initial_states or zero, through TMEM so that the hot loop below has one source
           const int64_t ibase = sn.b * a.i_b + (int64_t)(sn.h0 + hh) * a.i_h + (int64_t)p * a.i_p;
 #pragma unroll 1
@@ -875,7 +931,12 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             for (int e = 0; e < 16; ++e) v[e] = a.init ? __float_as_uint(ld_any(a.init, a.init_dtype, ibase + 16 * k16 + e)) : 0u;
             tmem_st16(tmem_addr(tb, w * 32, TM_S + 16 * k16), v);
           }
+          }
           tmem_st_wait();
+        }
+        if (sn.c + 1 == sn.cend) {  // this unit ends with this step
+          pend = sn.cend < nchunks ? 2 : 1;
+          pend_b = sn.b; pend_h0 = sn.h0;
         }
         const float2 dd = make_float2(dch, dch);
 #pragma unroll 1
@@ -922,22 +983,10 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         it_next(sn);
       }
     }
-    if (total > 0 && a.fin) {  // final state of the last item
+    if (total > 0 && pend) {  // state of the last unit
       wait1(B_U_DONE, (total - 1) & 1);
       tc_fence_after();
-      ChunkIter fl;
-      it_set(fl, blockIdx.x + (my_items - 1) * gridDim.x);
-      float* dst = a.fin + ((int64_t)(fl.b * a.H + fl.h0 + hh) * HD + p) * NS;
-#pragma unroll 1
-      for (int k4 = 0; k4 < 4; ++k4) {
-        uint32_t v[32];
-        tmem_ld32(tmem_addr(tb, w * 32, TM_S + 32 * k4), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          *reinterpret_cast<float4*>(dst + 32 * k4 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                                      __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-      }
+      store_unit_state();
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
@@ -1030,7 +1079,7 @@ namespace {
 int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const omni_tensor_t& A, const omni_tensor_t& D,
               const omni_tensor_t& dt_bias, const omni_tensor_t& init, const omni_tensor_t& fin, const omni_tensor_t& o,
               const void* wsB, const void* wsC, void* ws_states, int64_t G, int dt_softplus, float dt_min, float dt_max,
-              cudaStream_t s) {
+              cudaStream_t s, float* hand = nullptr, int* flags = nullptr) {
   const int64_t Bsz = x.shape[0], L = x.shape[1], H = x.shape[2];
   const int64_t nchunks = (L + Q - 1) / Q;
   OMNI_CHECK(present(dt) && shape_is(dt, 3, Bsz, L, H) && is_float_dtype(dt.dtype), OMNI_BAD_SHAPE, "ssd: dt must be (B, L, H)");
@@ -1070,6 +1119,7 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   a.B = (int)Bsz; a.L = (int)L; a.H = (int)H; a.G = (int)G;
   a.dt_softplus = dt_softplus; a.dt_min = dt_min; a.dt_max = dt_max;
   a.trace = mode == g_trace_mode ? g_trace : nullptr; a.trace_chunks = g_trace_chunks;
+  a.hand = hand; a.flags = flags;
 
   auto tmap4 = [&](CUtensorMap* m, const void* base, const int64_t* shape, const int64_t* stride, bool bf16, int rows) -> int {
     // dims innermost first: (inner, dim2, L, B); a size-1 dim may carry any stride: give TMA a harmless legal one
@@ -1111,6 +1161,9 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   });
   const int nitems = (int)(Bsz * (H / 2));
   const int grid = nitems < sm_count() ? nitems : sm_count();
+  if (flags != nullptr) {  // hand-off flags of the half-item schedule (a memset node under graph capture)
+    if (cudaMemsetAsync(flags, 0, kHandSlots * sizeof(int), s) != cudaSuccess) { flags = nullptr; a.hand = nullptr; a.flags = nullptr; }
+  }
   ssd_tc_fwd_kernel<<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
   OMNI_CUDA_LAUNCH_CHECK("ssd_tc_fwd_kernel");
   return OMNI_OK;
@@ -1126,8 +1179,12 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
   __half* wsB = static_cast<__half*>(p->workspace.data);
   __half* wsC = wsB + Bsz * L * G * NS;
   if (int rc = ssd_tc_prep(Bm, Cm, wsB, wsC, s)) return rc;
+  char* tail = reinterpret_cast<char*>(wsC + Bsz * L * G * NS);
+  tail += (256 - reinterpret_cast<uintptr_t>(tail) % 256) % 256;
+  float* hand = reinterpret_cast<float*>(tail);
+  int* flags = reinterpret_cast<int*>(tail + (size_t)kHandSlots * 128 * NS * sizeof(float));
   return tc_launch(0, x, p->dt, p->A, p->D, p->dt_bias, p->initial_states, p->final_states, o, wsB, wsC, nullptr, G,
-                   p->dt_softplus, p->dt_min, p->dt_max, s);
+                   p->dt_softplus, p->dt_min, p->dt_max, s, hand, flags);
 }
 
 // State sweeps for the backward (ssd_tc_bwd.cu): mode 1 = forward states from (x, fp16 B), mode 2 = reverse sweep of the
@@ -1156,5 +1213,6 @@ extern "C" void omni_debug_set_trace(void* buf, int chunks) {
 extern "C" int64_t omni_ssd_fwd_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim, int64_t ngroups,
                                                 int64_t dstate) {
   (void)nheads; (void)headdim;
-  return 2 * batch * seqlen * ngroups * dstate * 2;
+  // fp16 copies of B and C + the hand-off slots (fp32 state of a head pair) and flags of the half-item schedule
+  return 2 * batch * seqlen * ngroups * dstate * 2 + 256 + (int64_t)omni::kHandSlots * (128 * 128 * 4 + 4);
 }

@@ -153,6 +153,31 @@ def test_ssd_tc_matches_recurrent_at_bench_size():
     assert e < 1e-3 and ef < 3e-3
 
 
+@pytest.mark.parametrize("B,L,H", [(5, 633, 64), (3, 300, 128), (10, 129, 32)])
+def test_ssd_tc_half_item_schedule(B, L, H):
+    """More items than SMs with a remainder of at most half the grid: the left-over items are cut into two half sequences
+    handed over through the fp32 state slots (odd chunk counts, initial and final states included).  Reference: the exact
+    fp32 SIMT recurrence on the device (oracle-checked in test_gpu_parity.py)."""
+    from omnimamba_b200.interface.ssd_combined import ssd_fwd_raw
+    g = torch.Generator(device=DEV).manual_seed(B * L)
+    P, N = 64, 128
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g).bfloat16()
+    x, dt, Bm, Cm = rn(B, L, H, P), rn(B, L, H), rn(B, L, 1, N), rn(B, L, 1, N)
+    A = -(torch.rand(H, device=DEV, generator=g) * 15 + 1)
+    dt_bias = torch.rand(H, device=DEV, generator=g) * 4 - 6
+    D = torch.ones(H, device=DEV)
+    init = torch.randn(B, H, P, N, device=DEV, generator=g)
+    kw = dict(D=D, dt_bias=dt_bias, dt_softplus=True, initial_states=init, return_final_states=True)
+    o1, f1 = ssd_fwd_raw(x, dt, A, Bm, Cm, 256, algo="recurrent", **kw)
+    o2, f2 = ssd_fwd_raw(x, dt, A, Bm, Cm, 256, algo="chunked_tc", **kw)
+    o3, f3 = ssd_fwd_raw(x, dt, A, Bm, Cm, 256, algo="chunked_tc", **kw)  # (flags are reset per launch)
+    torch.cuda.synchronize()
+    e, ef = rel_l2(o2, o1), rel_l2(f2, f1)
+    print(f"half-item schedule B={B} L={L} H={H}: out {e:.2e} final {ef:.2e}")
+    assert e < 1e-3 and ef < 3e-3
+    assert torch.equal(o2, o3) and torch.equal(f2, f3)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # tensor-core chunked SSD backward (state sweeps + per-chunk gradient kernel) vs the oracle's autograd
 # ------------------------------------------------------------------------------------------------------------
