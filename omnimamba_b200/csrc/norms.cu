@@ -459,6 +459,62 @@ __global__ void __launch_bounds__(kThreads) add_norm_fwd_kernel(AddNormArgs a) {
   }
 }
 
+// ---- fast path of the fused residual-add + RMSNorm forward (Block.forward, /root/reference/models/stage2/block.py:86-95) -
+// x in a 16-bit type, residual / residual_out fp32 (residual_in_fp32=True) or absent, y in x's type, no bias, D = 8 columns
+// per thread (1024 / 2048 / 4096).  Persistent CTAs: weight columns in registers, the next row's x and residual vectors in
+// flight during the reduction and the stores, one __syncthreads per row.
+template <typename T>
+__global__ void __launch_bounds__(512) add_rms_fast_kernel(AddNormArgs a) {
+  __shared__ float red[2][16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int col = tid * 8;
+  float w[8];
+  ld8<true>(a.w, a.w_dtype, col, 8, w);
+  const T* xb = static_cast<const T*>(a.x.p);
+  const float* rb = static_cast<const float*>(a.res.p);
+  uint4 rx;
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+  auto load = [&](int64_t r) {
+    rx = __ldg(reinterpret_cast<const uint4*>(xb + r * a.x.rs + col));
+    if (rb) {
+      r0 = __ldg(reinterpret_cast<const float4*>(rb + r * a.res.rs + col));
+      r1 = __ldg(reinterpret_cast<const float4*>(rb + r * a.res.rs + col + 4));
+    }
+  };
+  int64_t row = blockIdx.x;
+  if (row < a.M) load(row);
+  const float inv_d = 1.f / (float)a.D;
+#pragma unroll 1
+  for (int it = 0; row < a.M; row += gridDim.x, ++it) {
+    float v[8];
+    unpack8<T>(rx, v);
+    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    const int64_t nrow = row + gridDim.x;
+    if (nrow < a.M) load(nrow);
+    if (a.res_out.p) {
+      float* ro = static_cast<float*>(a.res_out.p) + row * a.res_out.rs + col;
+      *reinterpret_cast<float4*>(ro) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(ro + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    float s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s2 = fmaf(v[k], v[k], s2);
+    s2 = warp_sum(s2);
+    if (lane == 0) red[it & 1][warp] = s2;
+    __syncthreads();
+    float tot = 0.f;
+    for (int k = 0; k < nwarps; ++k) tot += red[it & 1][k];
+    const float rstd = rsqrtf(tot * inv_d + a.eps);
+    if (tid == 0 && a.rstd) a.rstd[row] = rstd;
+    uint4 o;
+    o.x = pack2<T>(v[0] * rstd * w[0], v[1] * rstd * w[1]);
+    o.y = pack2<T>(v[2] * rstd * w[2], v[3] * rstd * w[3]);
+    o.z = pack2<T>(v[4] * rstd * w[4], v[5] * rstd * w[5]);
+    o.w = pack2<T>(v[6] * rstd * w[6], v[7] * rstd * w[7]);
+    *reinterpret_cast<uint4*>(static_cast<T*>(a.y.p) + row * a.y.rs + col) = o;
+  }
+}
+
 template <bool VEC, int NCH>
 __global__ void __launch_bounds__(kThreads) add_norm_bwd_kernel(AddNormArgs a) {
   __shared__ float red[32];
@@ -714,6 +770,17 @@ extern "C" int omni_add_norm_fwd(const omni_add_norm_fwd_params_t* p, void* stre
                    rows_vec_ok(p->residual_out, D) && rows_vec_ok(p->weight, D) && rows_vec_ok(p->bias, D);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nch = (int)(((D) + kThreads * 8 - 1) / (kThreads * 8));
+  // fast path: RMSNorm, 16-bit x / y of one type, fp32 (or no) residual in and fp32 (or no) residual out, no bias
+  if (vec && a.is_rms && !present(p->bias) && !present(p->mean) && (D == 1024 || D == 2048 || D == 4096) &&
+      p->x.dtype != OMNI_F32 && p->y.dtype == p->x.dtype && (!present(p->residual) || p->residual.dtype == OMNI_F32) &&
+      (!present(p->residual_out) || p->residual_out.dtype == OMNI_F32)) {
+    const unsigned threads = (unsigned)(D / 8);
+    const unsigned gridp = (unsigned)std::min<int64_t>(M, (int64_t)sm_count() * (2048 / threads));
+    if (p->x.dtype == OMNI_BF16) add_rms_fast_kernel<__nv_bfloat16><<<gridp, threads, 0, s>>>(a);
+    else add_rms_fast_kernel<__half><<<gridp, threads, 0, s>>>(a);
+    OMNI_CUDA_LAUNCH_CHECK("add_rms_fast_kernel");
+    return OMNI_OK;
+  }
 #define OMNI_LAUNCH_NCH(V, N) add_norm_fwd_kernel<V, N><<<(unsigned)M, kThreads, 0, s>>>(a)
   if (vec) { if (nch <= 1) OMNI_LAUNCH_NCH(true, 1); else if (nch == 2) OMNI_LAUNCH_NCH(true, 2); else OMNI_LAUNCH_NCH(true, 4); }
   else { if (nch <= 1) OMNI_LAUNCH_NCH(false, 1); else if (nch == 2) OMNI_LAUNCH_NCH(false, 2); else OMNI_LAUNCH_NCH(false, 4); }

@@ -25,20 +25,23 @@ def peak():
 
 
 def timeit(fn, steps=20, warmup=5, flush=None):
-    for _ in range(warmup):
-        fn()
-    torch.cuda.synchronize()
-    tot = 0.0
-    for _ in range(steps):
-        if flush is not None:
-            flush.zero_()
+    """`steps` launches back to back between two events (host-side wrapper time overlaps the previous launch); with `flush`
+    an L2-sized memset runs before every launch and its own time, measured the same way, is subtracted."""
+    def loop(body):
+        for _ in range(warmup):
+            body()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(steps):
+            body()
         e1.record()
         torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    return tot / steps / 1e3
+        return e0.elapsed_time(e1) / steps / 1e3
+    if flush is None:
+        return loop(fn)
+    both = loop(lambda: (flush.zero_(), fn()))
+    return max(both - loop(lambda: flush.zero_()), 1e-9)
 
 
 def main():
@@ -80,10 +83,10 @@ def main():
     del yn, dyn, yg, zg
 
     # f1 fused residual add + RMSNorm (block.py:86-95): x bf16 + residual fp32 -> y bf16 + residual fp32
-    xh, res, w2 = rn(B * L // 4, 2048), rn(B * L // 4, 2048, dtype=torch.float32), torch.ones(2048, device=dev)
+    xh, res, w2 = rn(B * L, 2048), rn(B * L, 2048, dtype=torch.float32), torch.ones(2048, device=dev)
     t = timeit(lambda: layer_norm_fn(xh, w2, None, residual=res, prenorm=True, residual_in_fp32=True, eps=1e-5, is_rms_norm=True))
-    by = (B * L // 4) * 2048 * (2 + 4 + 2 + 4)
-    out.append(dict(op="layer_norm_fn add+rmsnorm prenorm fwd (16384 rows x 2048)", ms=t * 1e3, bytes=by))
+    by = (B * L) * 2048 * (2 + 4 + 2 + 4)
+    out.append(dict(op="layer_norm_fn add+rmsnorm prenorm fwd (65536 rows x 2048)", ms=t * 1e3, bytes=by))
 
     # a8 selective_state_update, batch 64, fp32 state, stride-0 broadcast operands exactly as Mamba2.step passes them
     Bd = 64
