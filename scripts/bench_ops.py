@@ -17,6 +17,7 @@ sys.path.insert(0, ROOT)
 from omnimamba_b200.interface import causal_conv1d_fn, causal_conv1d_update, selective_state_update  # noqa: E402
 from omnimamba_b200.interface.layer_norm import layer_norm_fn  # noqa: E402
 from omnimamba_b200.interface.layernorm_gated import rmsnorm_fn  # noqa: E402
+from omnimamba_b200.interface.ssd_combined import mamba_split_conv1d_scan_combined  # noqa: E402
 
 
 def peak():
@@ -81,6 +82,34 @@ def main():
     t = timeit(lambda: torch.autograd.grad(yn, (yg, zg, nwg), dyn, retain_graph=True))
     out.append(dict(op="rmsnorm_fn gated bwd (65536 rows x 4096; incl. torch partial-sum reduction)", ms=t * 1e3, bytes=5 * B * L * d_inner * 2))
     del yn, dyn, yg, zg
+
+    # a2 the fused training op without out_proj (conv1d + SiLU -> SSD -> gated RMSNorm): SURVEY 8(d) secondary figure,
+    # 25 216 B/token forward (read zxbcdt 17 024, write y 8 192); fwd+bwd adds dy 8 192 + re-read 17 024 + dzxbcdt 17 024
+    import math
+    dt0 = torch.exp(torch.rand(H, device=dev, generator=g) * (math.log(0.1) - math.log(1e-3)) + math.log(1e-3)).clamp(min=1e-4)
+    dtb_f = dt0 + torch.log(-torch.expm1(-dt0))
+    A_f = -(torch.rand(H, device=dev, generator=g) * 15 + 1)
+    D_f = torch.ones(H, device=dev)
+    fused = lambda zz: mamba_split_conv1d_scan_combined(zz, w, b, dtb_f, A_f, D_f, 256, activation="silu", rmsnorm_weight=nw,
+                                                        rmsnorm_eps=1e-5, outproj_weight=None, headdim=P, ngroups=1,
+                                                        norm_before_gate=False)
+    with torch.no_grad():
+        t = timeit(lambda: fused(zx), steps=10)
+    out.append(dict(op="mamba_split_conv1d_scan_combined fwd, no out_proj (B=16, L=4096, d_model=2048)", ms=t * 1e3,
+                    bytes=B * L * 25216, tokens_per_s=B * L / t))
+    zg2 = zx.detach().requires_grad_()
+    wg2, bg2, nwg2 = w.clone().requires_grad_(), b.clone().requires_grad_(), nw.clone().requires_grad_()
+    dtbg, Ag, Dg = dtb_f.clone().requires_grad_(), A_f.clone().requires_grad_(), D_f.clone().requires_grad_()
+    dyf = rn(B, L, d_inner)
+
+    def fused_fb():
+        yy = mamba_split_conv1d_scan_combined(zg2, wg2, bg2, dtbg, Ag, Dg, 256, activation="silu", rmsnorm_weight=nwg2,
+                                              rmsnorm_eps=1e-5, outproj_weight=None, headdim=P, ngroups=1, norm_before_gate=False)
+        torch.autograd.grad(yy, (zg2, wg2, bg2, dtbg, Ag, Dg, nwg2), dyf)
+    t = timeit(fused_fb, steps=5, warmup=2)
+    out.append(dict(op="mamba_split_conv1d_scan_combined fwd+bwd, no out_proj (same shape)", ms=t * 1e3,
+                    bytes=B * L * (25216 + 8192 + 17024 + 17024), tokens_per_s=B * L / t))
+    del zg2, dyf
 
     # f1 fused residual add + RMSNorm (block.py:86-95): x bf16 + residual fp32 -> y bf16 + residual fp32
     xh, res, w2 = rn(B * L, 2048), rn(B * L, 2048, dtype=torch.float32), torch.ones(2048, device=dev)
