@@ -156,12 +156,19 @@ __global__ void __launch_bounds__(32 * kWarps) ssu_kernel(SsuArgs a) {
 // ---- fast path: A tied over d_state (Mamba-2), d_state = 128, headdim a multiple of 16 --------------------------------
 // The kernel above recomputes every per-row scalar (dt transform, exp, D x, silu(z)) in all 32 lanes and reduces each row
 // with its own 5-step shuffle tree: ~60 instructions per state element, instruction-bound at 43 % of the HBM roofline (ncu).
-// Here a warp owns 16 rows of one (batch, head): lane r < 16 computes the scalars of row r once and broadcasts them by
-// shuffle, all 16 state rows (8 KB fp32) are in flight before the first is used, and the 16 per-lane partial sums of
-// <state, C> are reduced together by a transposing butterfly (16 shuffles instead of 80).
+// Here a warp owns 16 (fp32 state) or 32 (16-bit state) rows of one (batch, head): lane r computes the scalars of row r once
+// and broadcasts them by shuffle, all rows (8 KB) are in flight before the first is used, and the per-lane partial sums of
+// <state, C> are reduced together by a transposing butterfly (16 / 31 shuffles instead of 80 / 160).
+template <typename TS> struct RawRow;   // one lane's 4 state elements of a row, as loaded
+template <> struct RawRow<float> { using type = float4; };
+template <> struct RawRow<__nv_bfloat16> { using type = uint2; };
+template <> struct RawRow<__half> { using type = uint2; };
+template <typename TS> constexpr int tied_rows() { return sizeof(TS) == 4 ? 16 : 32; }  // 8 KB of state per warp in flight
+
 template <typename TS>
 __global__ void __launch_bounds__(32 * kWarps) ssu_tied_kernel(SsuArgs a) {
-  constexpr int R = 16;
+  constexpr int R = tied_rows<TS>();
+  using Raw = typename RawRow<TS>::type;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pblocks = a.P / R;
   const int64_t task = (int64_t)blockIdx.x * kWarps + warp;
@@ -172,18 +179,18 @@ __global__ void __launch_bounds__(32 * kWarps) ssu_tied_kernel(SsuArgs a) {
   const int g = h / (a.H / a.G);
   const int p0 = pb * R;
   const int n = lane * 4;
-  // state rows first: the longest latency
+  // state rows first: the longest latency (kept as loaded, converted when used)
   TS* sbase = static_cast<TS*>(a.state) + b * a.st_b + h * a.st_h + (int64_t)p0 * a.st_p + n;
-  float S[R][4];
+  Raw raw[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) ld4<TS>(sbase + r * a.st_p, S[r]);
+  for (int r = 0; r < R; ++r) raw[r] = *reinterpret_cast<const Raw*>(sbase + r * a.st_p);
   float Bv[4], Cv[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     Bv[e] = ld_any(a.Bm, a.bc_dtype, b * a.B_b + g * a.B_g + n + e);
     Cv[e] = ld_any(a.Cm, a.bc_dtype, b * a.C_b + g * a.C_g + n + e);
   }
-  // per-row scalars, one row per lane (lanes 16..31 mirror rows 0..15)
+  // per-row scalars, one row per lane (R = 16: lanes 16..31 mirror rows 0..15)
   const int p = p0 + (lane & (R - 1));
   float dtv = ld_any(a.dt, a.dt_dtype, b * a.dt_b + h * a.dt_h + p * a.dt_p);
   if (a.dt_bias) dtv += ld_any(a.dt_bias, a.db_dtype, h * a.db_h + p * a.db_p);
@@ -195,23 +202,25 @@ __global__ void __launch_bounds__(32 * kWarps) ssu_tied_kernel(SsuArgs a) {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const float dA = __shfl_sync(0xffffffffu, dA_l, r), dtx = __shfl_sync(0xffffffffu, dtx_l, r);
+    float S[4];
+    if constexpr (sizeof(TS) == 4) { S[0] = raw[r].x; S[1] = raw[r].y; S[2] = raw[r].z; S[3] = raw[r].w; }
+    else ld4<TS>(reinterpret_cast<const TS*>(&raw[r]), S);
     float sum = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float sv = fmaf(S[r][e], dA, dtx * Bv[e]);
-      S[r][e] = sv;
-      sum = fmaf(sv, Cv[e], sum);
+      S[e] = fmaf(S[e], dA, dtx * Bv[e]);
+      sum = fmaf(S[e], Cv[e], sum);
     }
-    st4<TS>(sbase + r * a.st_p, S[r]);
+    st4<TS>(sbase + r * a.st_p, S);
     acc[r] = sum;
   }
-  // transposing butterfly: after the xor-16/8/4/2 steps every lane holds ONE row's sum over 16 lanes, the xor-1 step
-  // completes it; row index = bits 4..1 of the lane
+  // transposing butterfly: each xor step halves the rows a lane carries and doubles the lanes summed; with R = 32 the five
+  // steps leave lane l with the complete sum of row l, with R = 16 lane l holds row l >> 1 and one more xor-1 step completes it
 #pragma unroll
-  for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+  for (int half = R / 2, off = 16; half >= 1; half >>= 1, off >>= 1) {
     const bool up = (lane & off) != 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < R / 2; ++j) {
       if (j < half) {
         const float send = up ? acc[j] : acc[j + half];
         const float recv = __shfl_xor_sync(0xffffffffu, send, off);
@@ -219,11 +228,14 @@ __global__ void __launch_bounds__(32 * kWarps) ssu_tied_kernel(SsuArgs a) {
       }
     }
   }
-  float y = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
-  const int row = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-  // the scalars of `row` live in lane `row`
-  const float x_r = __shfl_sync(0xffffffffu, xv, row);
-  if ((lane & 1) == 0) {
+  float y = acc[0];
+  int row = lane;
+  if constexpr (R == 16) {
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    row = lane >> 1;
+  }
+  const float x_r = __shfl_sync(0xffffffffu, xv, row);  // (the scalars of `row` live in lane `row`)
+  if (R == 32 || (lane & 1) == 0) {
     const int pr = p0 + row;
     if (a.D) y = fmaf(x_r, ld_any(a.D, a.D_dtype, h * a.D_h + pr * a.D_p), y);
     if (a.z) y *= silu_f(ld_any(a.z, a.x_dtype, b * a.z_b + h * a.z_h + pr * a.z_p));
@@ -234,8 +246,8 @@ __global__ void __launch_bounds__(32 * kWarps) ssu_tied_kernel(SsuArgs a) {
 template <typename TS>
 int launch(const SsuArgs& a, cudaStream_t s) {
   const bool tie = a.A_n == 0;
-  if (tie && a.N == 128 && a.P % 16 == 0 && a.P > 0) {
-    const int64_t tasks16 = (int64_t)a.B * a.H * (a.P / 16);
+  if (tie && a.N == 128 && a.P % tied_rows<TS>() == 0 && a.P > 0) {
+    const int64_t tasks16 = (int64_t)a.B * a.H * (a.P / tied_rows<TS>());
     ssu_tied_kernel<TS><<<(unsigned)((tasks16 + kWarps - 1) / kWarps), 32 * kWarps, 0, s>>>(a);
     OMNI_CUDA_LAUNCH_CHECK("ssu_tied_kernel");
     return OMNI_OK;
