@@ -156,7 +156,7 @@ template <> __device__ __forceinline__ uint2 pack4<__half>(const float (&o)[4]) 
 }
 
 template <typename T, bool SILU>
-__global__ void __launch_bounds__(32 * kSegs, 8) conv1d_fwd_fast_kernel(ConvArgs a) {
+__global__ void __launch_bounds__(32 * kSegs, 6) conv1d_fwd_fast_kernel(ConvArgs a) {
   const int d0 = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int b = blockIdx.z;
   const int t0 = (blockIdx.y * kSegs + threadIdx.y) * kTLF;
@@ -190,6 +190,14 @@ __global__ void __launch_bounds__(32 * kSegs, 8) conv1d_fwd_fast_kernel(ConvArgs
   };
   const int n = min(kTLF, a.L - t0);
   int i = 0;
+#pragma unroll 1
+  for (; i + 16 <= n; i += 16) {  // 16 tokens (128 B per thread) in flight: ~100 KB per SM at 24 resident warps
+    uint2 raw[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) raw[u] = __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(i + u) * a.xs_l));
+#pragma unroll
+    for (int u = 0; u < 16; ++u) token(raw[u], op + (int64_t)(i + u) * a.os_l);
+  }
 #pragma unroll 1
   for (; i + 8 <= n; i += 8) {
     uint2 raw[8];
