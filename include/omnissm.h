@@ -114,7 +114,9 @@ typedef struct omni_ssd_fwd_params {
   omni_tensor_t x, dt, A, B, C, D, z, dt_bias, initial_states, seq_idx;
   omni_tensor_t out, final_states;
   omni_tensor_t workspace; /* 1-D, contiguous, >= omni_ssd_fwd_workspace_bytes() bytes, 16B aligned; needed by the
-                            * tensor-core algorithm (AUTO falls back to the recurrence without it) */
+                            * tensor-core algorithm (AUTO falls back to the recurrence without it).  It holds the fp16
+                            * copies of B and C and the fp32 state hand-off slots + flags of the half-item schedule
+                            * (the flags are reset by a memset on `stream` inside the call); contents are scratch */
   int32_t chunk_size; /* accepted for API parity; the result does not depend on it */
   int32_t dt_softplus;
   float dt_min, dt_max; /* dt_limit */
