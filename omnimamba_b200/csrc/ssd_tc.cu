@@ -1191,11 +1191,17 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
 // state gradients from (dy, fp16 C).  `init` seeds the recurrence, `fin` (fp32, optional) receives its last state.
 int ssd_tc_state_sweep(int mode, const omni_tensor_t& xlike, const omni_tensor_t& dt, const omni_tensor_t& A,
                        const omni_tensor_t& dt_bias, const omni_tensor_t& init, const omni_tensor_t& fin, const void* ws_bslot,
-                       void* ws_states, int64_t G, int dt_softplus, float dt_min, float dt_max, cudaStream_t s) {
+                       void* ws_states, int64_t G, int dt_softplus, float dt_min, float dt_max, cudaStream_t s,
+                       void* hand_slots) {
   omni_tensor_t none{};
+  float* hand = static_cast<float*>(hand_slots);
+  int* flags = hand_slots ? reinterpret_cast<int*>(static_cast<char*>(hand_slots) + (size_t)kHandSlots * 128 * NS * sizeof(float))
+                          : nullptr;
   return tc_launch(mode, xlike, dt, A, none, dt_bias, init, fin, none, ws_bslot, nullptr, ws_states, G, dt_softplus, dt_min,
-                   dt_max, s);
+                   dt_max, s, hand, flags);
 }
+
+int64_t ssd_tc_hand_bytes() { return (int64_t)kHandSlots * (128 * NS * (int64_t)sizeof(float) + sizeof(int)) + 256; }
 
 }  // namespace omni
 

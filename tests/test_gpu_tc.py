@@ -234,3 +234,31 @@ def test_ssd_tc_bwd(batch, L, H, G, variant):
         # dA / ddt_bias: the reverse cumulative sums inside a chunk make the fp16 operand rounding of neighbouring tokens
         # correlated, so these sums over (batch, time) get 3e-2 (upstream's own bf16 tolerance for them is rtol 3e-2 too)
         assert v < (3e-2 if k in ("dA", "ddt_bias") else 1e-2), (k, v)
+
+
+@pytest.mark.parametrize("B,L,H", [(5, 633, 64), (3, 300, 128)])
+def test_ssd_tc_bwd_half_item_schedule(B, L, H):
+    """The state sweeps of the backward with the half-item schedule (more items than SMs, odd chunk counts, initial states,
+    a gradient flowing into the final states): tensor-core backward against the exact fp32 SIMT backward on the device."""
+    from omnimamba_b200.interface.ssd_combined import ssd_bwd_raw
+    g = torch.Generator(device=DEV).manual_seed(B + L)
+    P, N = 64, 128
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g).bfloat16()
+    x, dt, Bm, Cm, dy = rn(B, L, H, P), rn(B, L, H), rn(B, L, 1, N), rn(B, L, 1, N), rn(B, L, H, P)
+    A = -(torch.rand(H, device=DEV, generator=g) * 15 + 1)
+    dt_bias = torch.rand(H, device=DEV, generator=g) * 4 - 6
+    D = torch.ones(H, device=DEV)
+    init = torch.randn(B, H, P, N, device=DEV, generator=g)
+    dfin = torch.randn(B, H, P, N, device=DEV, generator=g) * 0.1
+    kw = dict(D=D, dt_bias=dt_bias, dt_softplus=True, initial_states=init, dfinal_states=dfin, want_dinitial=True)
+    ref = ssd_bwd_raw(dy, x, dt, A, Bm, Cm, 256, algo="recurrent", **kw)
+    got = ssd_bwd_raw(dy, x, dt, A, Bm, Cm, 256, algo="chunked_tc", **kw)
+    torch.cuda.synchronize()
+    names = ["dx", "ddt", "dA", "dB", "dC", "dD", "dz", "ddt_bias", "dinit"]
+    for nme, r, t in zip(names, ref, got):
+        if r is None:
+            continue
+        e = rel_l2(t, r)
+        print(f"bwd half-item schedule B={B} L={L} H={H}: {nme} {e:.2e}")
+        # (the per-head sums dA / ddt_bias cancel heavily: 3e-2 as in test_ssd_tc_bwd, upstream's own bf16 tolerance)
+        assert e < (3e-2 if nme in ("dA", "ddt_bias") else 1e-2), (nme, e)
