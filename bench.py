@@ -200,9 +200,19 @@ def main():
     dist_on = world > 1
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its banner / debug lines to stdout by default: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        torch.distributed.init_process_group("nccl", device_id=device)
+        # NCCL prints its banner / debug lines on stdout while the communicator is created: point fd 1 at stderr for that
+        # moment so that stdout carries only the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.distributed.init_process_group("nccl", device_id=device)
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from omnimamba_b200 import _cabi
     from omnimamba_b200.dist import allreduce_param_grads
