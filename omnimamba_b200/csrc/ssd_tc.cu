@@ -24,15 +24,19 @@
 // All accumulators, dt, L and the state are fp32.
 //
 // Warp roles (512 threads, 1 CTA per SM; TMEM lane quadrant = warp % 4):
-//   warp 0      TMA producer (x and C one stage, B two stages; 128B swizzle)          warp 1   tcgen05.mma issuer
-//   warps 2,3   per-head dt / cumsum / decay tables
+//   warps 0,1   per-head dt / cumsum / decay tables (dt gathers prefetched into L2, registers two chunks ahead)
+//   warp 2      TMA producer (x and C one stage, B two stages; 128B swizzle)          warp 3   tcgen05.mma issuer
 //   warps 4-11  P builders (two per quadrant, split by 32-column blocks), then the x pass (lane = row i of one head:
-//               x -> fp16 in place, X' = x dt decay -> second tile, D x -> the Ydiag accumulator in TMEM)
-//   warps 12-15 state keepers (S16 copy + decay rescale, lane = (h,p)) and epilogue (lane = row i; y staged per warp
-//               in swizzled shared memory and written with TMA stores)
-// Tensor-pipe order per chunk g:  CB(g) | Yoff(g) | S-update(g) | Ydiag(g): the three that only need TMA tiles and the
-// state run while the P builders work; C(g) is free after Yoff(g) and B(g) after the S-update, so their next loads land
-// before CB(g+1).
+//               x -> fp16 in place, X' = x dt decay -> second tile, D x -> the head's Ydiag accumulator in TMEM)
+//   warps 12-15 epilogue (lane = row i; y staged in two 2 KB 64B-swizzled slots per warp, TMA stores of 32 rows x 32
+//               columns) and then the state keepers (S16 copy + decay rescale, lane = (h,p))
+// Roles made of several warps let one warp watch the mbarrier and park the others on a named barrier (see `wait1`).
+// Tensor-pipe issue order per chunk g:  Yoff(g) | Ydiag_0(g) | Ydiag_1(g) | CB(g+1) | S-update(g).  The epilogue needs the
+// first three; CB(g+1) must follow Ydiag(g) (P is built in place over CB) and opens the longest dependent chain
+// CB -> P build -> x pass -> Ydiag; the state update has a whole chunk of slack.  Accumulators are released per head.
+// Modes 1 / 2 (state sweeps of the backward) run only table -> in-place tile scaling -> S-update -> state keeper, with
+// the x-like tile rotating through three stages (XA, XB, the C slot).
+// Work schedule: see the comment at `split` in the kernel (half-item hand-off for the left-over items).
 // TMEM columns: [0,128) CB then P in place | [128,256) S | [256,384) Yoff | [384,512) Ydiag (64 per head).
 #include <algorithm>
 #include <mutex>
