@@ -53,6 +53,9 @@ constexpr int NS = 128;    // d_state
 // Warps that watch mbarriers for their role sit on schedulers 2 and 3 (with the TMA / MMA threads); the table warps (0, 1),
 // whose serial dt -> cumsum -> exp chain feeds every chunk, share their schedulers with no spinning warp.
 constexpr int kLeadPX = 2, kLeadE = 3;
+// (measured: storing y with 16-byte global stores straight from registers instead of the staged TMA stores makes the
+// epilogue AND the concurrent P build slower - 32 scattered rows per store instruction load the LSU: 0.52 vs 0.49 ms)
+constexpr bool kDirectY = false;
 constexpr int kHandSlots = 128;  // hand-off slots of the half-item schedule (>= grid / 2)
 constexpr int kThreads = 512;   // 16 warps: 2 table, TMA, MMA, 8 P build + x pass, 4 epilogue + state
 
@@ -837,7 +840,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           uint32_t v0[32], v1[32];
           tmem_ld32(tmem_addr(tb, w * 32, TM_YOFF + 32 * s4), v0);
           tmem_ld32(tmem_addr(tb, w * 32, TM_YD + 32 * s4), v1);
-          if (a.out_dtype == OMNI_BF16) {  // the slot is free once the store issued two steps ago has read it
+          if (!kDirectY && a.out_dtype == OMNI_BF16) {  // the slot is free once the store issued two steps ago has read it
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
           }
@@ -855,7 +858,16 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               if (hx == 1) mbar_arrive(&bars[B_TAB_FREE + st]);
             }
           }
-          if (a.out_dtype == OMNI_BF16) {
+          if (kDirectY && a.out_dtype == OMNI_BF16) {
+            if (t < a.L) {
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + eb * a.o_b + (int64_t)t * a.o_l +
+                                                    (int64_t)(eh0 + hx) * a.o_h + 32 * half);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                dst[k] = make_uint4(pack_bf16(y[4 * k].x, y[4 * k].y), pack_bf16(y[4 * k + 1].x, y[4 * k + 1].y),
+                                    pack_bf16(y[4 * k + 2].x, y[4 * k + 2].y), pack_bf16(y[4 * k + 3].x, y[4 * k + 3].y));
+            }
+          } else if (a.out_dtype == OMNI_BF16) {
             uint8_t* yrow = slot + lane * 64;
             const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
