@@ -177,6 +177,7 @@ struct ChunkIter {
 // Code size matters here: sixteen warps run five different role loops, and with everything unrolled the kernel was 130 KB
 // of SASS - far beyond the 32 KB instruction cache level - so a third of all issue slots were lost to instruction
 // fetch (ncu stall_no_inst).  Inner loops are therefore kept rolled (#pragma unroll 1) wherever the body is large.
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapY,
@@ -265,7 +266,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   auto it_next = [&](ChunkIter& it) {
     if (++it.c == it.cend) it_set(it, it.u + 1);
   };
-  const int mode = a.mode;
+  constexpr int mode = MODE;  // (one instantiation per mode: the forward does not carry the sweeps' code and vice versa)
   auto cphys = [&](int c) { return mode == 2 ? nchunks - 1 - c : c; };  // chunk visited at step c of an item
 
   if (warp == 2) {
@@ -1173,14 +1174,18 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   int dev = 0;
   cudaGetDevice(&dev);
   std::call_once(once[dev & 63], [] {
-    cudaFuncSetAttribute(ssd_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(ssd_tc_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(ssd_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(ssd_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
   });
   const int nitems = (int)(Bsz * (H / 2));
   const int grid = nitems < sm_count() ? nitems : sm_count();
   if (flags != nullptr) {  // hand-off flags of the half-item schedule (a memset node under graph capture)
     if (cudaMemsetAsync(flags, 0, kHandSlots * sizeof(int), s) != cudaSuccess) { flags = nullptr; a.hand = nullptr; a.flags = nullptr; }
   }
-  ssd_tc_fwd_kernel<<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+  if (mode == 0) ssd_tc_fwd_kernel<0><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+  else if (mode == 1) ssd_tc_fwd_kernel<1><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+  else ssd_tc_fwd_kernel<2><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
   OMNI_CUDA_LAUNCH_CHECK("ssd_tc_fwd_kernel");
   return OMNI_OK;
 }
