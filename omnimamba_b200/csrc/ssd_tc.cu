@@ -115,10 +115,13 @@ struct TcArgs {
 };
 
 // trace slot layout: trace[g * 32 + event]
-#define TR(ev)                                                                          \
-  do {                                                                                  \
-    if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (int)g < a.trace_chunks)  \
-      a.trace[g * 32 + (ev)] = clock64();                                               \
+// (compiled in only in the TRACE instantiations: the untraced kernels do not carry the ~30 probe sites)
+#define TR(ev)                                                                                    \
+  do {                                                                                            \
+    if constexpr (TRACE) {                                                                        \
+      if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (int)g < a.trace_chunks)          \
+        a.trace[g * 32 + (ev)] = clock64();                                                       \
+    }                                                                                             \
   } while (0)
 
 __device__ __forceinline__ float ex2f(float v) {
@@ -177,7 +180,7 @@ struct ChunkIter {
 // Code size matters here: sixteen warps run five different role loops, and with everything unrolled the kernel was 130 KB
 // of SASS - far beyond the 32 KB instruction cache level - so a third of all issue slots were lost to instruction
 // fetch (ncu stall_no_inst).  Inner loops are therefore kept rolled (#pragma unroll 1) wherever the body is large.
-template <int MODE>
+template <int MODE, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapY,
@@ -467,9 +470,8 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     auto chunk_ptr = [&](const ChunkIter& it) -> const char* {  // this lane's first token of the chunk
       return dtbase + (it.b * a.dt_b + (int64_t)(it.h0 + hh) * a.dt_h) * esz + (int64_t)(cphys(it.c) * Q + lane * 4) * tstride;
     };
-    // raw dt bits are loaded TWO chunks ahead into two statically alternating register sets (the loop is unrolled by two)
-    uint32_t raw_a[4], raw_b[4];
-    auto load_raw = [&](uint32_t (&raw)[4], const ChunkIter& it, bool valid) {
+    uint32_t raw[4];  // raw dt bits of the NEXT chunk: loaded a chunk ahead (an L2 hit thanks to the prefetch), converted when used
+    auto load_raw = [&](const ChunkIter& it, bool valid) {
       const char* ptr = chunk_ptr(it);
       const int t0 = cphys(it.c) * Q + lane * 4;
 #pragma unroll
@@ -496,16 +498,16 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     ChunkIter it, itn, itp;
     it_set(it, 0);
     itn = it;
-    load_raw(raw_a, itn, total > 0);
-    it_next(itn);
-    load_raw(raw_b, itn, total > 1);
+    load_raw(itn, total > 0);
     itp = itn;
-    for (uint32_t k = 2; k <= 4 && k < total; ++k) {
+#pragma unroll 1
+    for (uint32_t k = 1; k <= 3 && k < total; ++k) {
       it_next(itp);
       prefetch_raw(itp);
     }
     float Ah2 = 0.f, bias = 0.f;
-    auto body = [&](uint32_t (&raw)[4], uint32_t g) {
+#pragma unroll 1
+    for (uint32_t g = 0; g < total; ++g) {
       const int c = cphys(it.c);
       const uint32_t st = g & 1, n = g >> 1;
       Tab* tab = reinterpret_cast<Tab*>(smem + SM_TAB) + st;
@@ -530,8 +532,8 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         lam[k] = run;
       }
       it_next(itn);
-      load_raw(raw, itn, g + 2 < total);  // raw dt of chunk g + 2 (this register set's next use)
-      if (g + 5 < total) {
+      load_raw(itn, g + 1 < total);  // next chunk's raw dt: in flight while this chunk's tables are built
+      if (g + 4 < total) {
         it_next(itp);
         prefetch_raw(itp);
       }
@@ -602,11 +604,6 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       if (hh == 0) TR(10);
       if (lane == 0) mbar_arrive(&bars[B_TAB_READY + st]);
       it_next(it);
-    };
-#pragma unroll 1
-    for (uint32_t g = 0; g < total; g += 2) {
-      body(raw_a, g);
-      if (g + 1 < total) body(raw_b, g + 1);
     }
   } else if (warp < 12) {
     // ============ P builders (lane = row i, 32-column blocks split between the two warps of a quadrant) ==============
@@ -945,7 +942,15 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           for (int k16 = 0; k16 < 8; ++k16) {
             uint32_t v[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = a.init ? __float_as_uint(ld_any(a.init, a.init_dtype, ibase + 16 * k16 + e)) : 0u;
+            for (int e = 0; e < 16; ++e) v[e] = 0u;
+            if (a.init != nullptr) {  // (cold: once per item; kept rolled so the dtype dispatch is not replicated 16 times)
+#pragma unroll 1
+              for (int e = 0; e < 16; ++e) {
+                const uint32_t bits = __float_as_uint(ld_any(a.init, a.init_dtype, ibase + 16 * k16 + e));
+#pragma unroll
+                for (int e2 = 0; e2 < 16; ++e2) v[e2] = e2 == e ? bits : v[e2];
+              }
+            }
             tmem_st16(tmem_addr(tb, w * 32, TM_S + 16 * k16), v);
           }
           }
@@ -1174,18 +1179,25 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   int dev = 0;
   cudaGetDevice(&dev);
   std::call_once(once[dev & 63], [] {
-    cudaFuncSetAttribute(ssd_tc_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    cudaFuncSetAttribute(ssd_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    cudaFuncSetAttribute(ssd_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(ssd_tc_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(ssd_tc_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(ssd_tc_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(ssd_tc_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(ssd_tc_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(ssd_tc_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
   });
   const int nitems = (int)(Bsz * (H / 2));
   const int grid = nitems < sm_count() ? nitems : sm_count();
   if (flags != nullptr) {  // hand-off flags of the half-item schedule (a memset node under graph capture)
     if (cudaMemsetAsync(flags, 0, kHandSlots * sizeof(int), s) != cudaSuccess) { flags = nullptr; a.hand = nullptr; a.flags = nullptr; }
   }
-  if (mode == 0) ssd_tc_fwd_kernel<0><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
-  else if (mode == 1) ssd_tc_fwd_kernel<1><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
-  else ssd_tc_fwd_kernel<2><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+  if (a.trace != nullptr) {  // debug instantiations with the probe sites
+    if (mode == 0) ssd_tc_fwd_kernel<0, true><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+    else if (mode == 1) ssd_tc_fwd_kernel<1, true><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+    else ssd_tc_fwd_kernel<2, true><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+  } else if (mode == 0) ssd_tc_fwd_kernel<0, false><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+  else if (mode == 1) ssd_tc_fwd_kernel<1, false><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+  else ssd_tc_fwd_kernel<2, false><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
   OMNI_CUDA_LAUNCH_CHECK("ssd_tc_fwd_kernel");
   return OMNI_OK;
 }
