@@ -129,6 +129,11 @@ __device__ __forceinline__ float ex2f(float v) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {
   uint32_t r;
@@ -362,7 +367,10 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
   } else if (warp == 3) {
     // ============ MMA issuer ==========================================================================================
-    if (lane == 0 && total > 0) {
+    // (warp-uniform control flow: every lane waits and computes the descriptors, one elected lane issues - the compiler then
+    // keeps the operands in uniform registers instead of funnelling per-thread registers through R2UR loops)
+    if (total > 0) {
+      const bool leader = elect_one();
       const uint32_t id_nn = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorK);
       const uint32_t id_u = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorMN, kMajorMN);
       const uint32_t id_yd = make_idesc(128, 64, kFmtF16, kFmtF16, kMajorK, kMajorMN);
@@ -385,9 +393,9 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           tc_fence_after();
           TR(5);
 #pragma unroll
-          for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + TM_S, dXs + k * 128, dBm + k * 128, id_u, true);
-          mma_commit(&bars[B_U_DONE]);
-          mma_commit(&bars[B_EMPTY_B + st]);
+          for (uint32_t k = 0; k < 8; ++k) if (leader) mma_ss(tb + TM_S, dXs + k * 128, dBm + k * 128, id_u, true);
+          if (leader) mma_commit(&bars[B_U_DONE]);
+          if (leader) mma_commit(&bars[B_EMPTY_B + st]);
           continue;
         }
         // Issue order per chunk: Yoff(g) | Ydiag(g) | CB(g+1) | S-update(g).  The epilogue only needs the first two, CB(g+1)
@@ -401,9 +409,9 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
           for (uint32_t k = 0; k < 8; ++k) {
             const uint32_t off = ((k >> 2) << 10) + ((k & 3) << 1);
-            mma_ss(tb + TM_CB, dC + off, dBk + off, id_nn, k > 0);
+            if (leader) mma_ss(tb + TM_CB, dC + off, dBk + off, id_nn, k > 0);
           }
-          mma_commit(&bars[B_CB_DONE]);
+          if (leader) mma_commit(&bars[B_CB_DONE]);
         }
         // Yoff = C S16^T  (state entering the chunk); first, so that C(g) is released early (its reload must land before
         // CB(g+1)) - it only needs the state copy and the accumulators the previous epilogue has read
@@ -417,9 +425,9 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
         for (uint32_t k = 0; k < 8; ++k) {
           const uint32_t off = ((k >> 2) << 10) + ((k & 3) << 1);
-          mma_ss(tb + TM_YOFF, dC + off, dS + off, id_nn, k > 0);
+          if (leader) mma_ss(tb + TM_YOFF, dC + off, dS + off, id_nn, k > 0);
         }
-        mma_commit(&bars[B_YOFF_DONE]);
+        if (leader) mma_commit(&bars[B_YOFF_DONE]);
         // Ydiag_h (+)= P_h x_h   (the accumulator already holds D x)
         wait1(B_P_READY, ph);
 #pragma unroll
@@ -429,10 +437,10 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           if (h == 0) TR(6);
 #pragma unroll
           for (uint32_t k = 0; k < 8; ++k)
-            mma_ts(tb + TM_YD + 64 * h, tb + TM_CB + 32 * (k >> 1) + 16 * h + 8 * (k & 1), dXA + h * 1024 + k * 128, id_yd,
+            if (leader) mma_ts(tb + TM_YD + 64 * h, tb + TM_CB + 32 * (k >> 1) + 16 * h + 8 * (k & 1), dXA + h * 1024 + k * 128, id_yd,
                    (has_D | k) != 0);
         }
-        mma_commit(&bars[B_YD_DONE]);
+        if (leader) mma_commit(&bars[B_YD_DONE]);
         // CB(g+1) = C B^T of the next chunk
         if (g + 1 < total) {
           const uint32_t st1 = (g + 1) & 1;
@@ -444,18 +452,18 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
           for (uint32_t k = 0; k < 8; ++k) {
             const uint32_t off = ((k >> 2) << 10) + ((k & 3) << 1);
-            mma_ss(tb + TM_CB, dC + off, dBk1 + off, id_nn, k > 0);
+            if (leader) mma_ss(tb + TM_CB, dC + off, dBk1 + off, id_nn, k > 0);
           }
-          mma_commit(&bars[B_CB_DONE]);
+          if (leader) mma_commit(&bars[B_CB_DONE]);
         }
         // S += X'^T B   (S was rescaled by exp(lam_last) by the state keepers; X16_READY: part (a) of the x pass)
         wait1(B_X16_READY, ph);
         tc_fence_after();
         TR(5);
 #pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + TM_S, dXB + k * 128, dBm + k * 128, id_u, true);
-        mma_commit(&bars[B_U_DONE]);
-        mma_commit(&bars[B_EMPTY_B + st]);
+        for (uint32_t k = 0; k < 8; ++k) if (leader) mma_ss(tb + TM_S, dXB + k * 128, dBm + k * 128, id_u, true);
+        if (leader) mma_commit(&bars[B_U_DONE]);
+        if (leader) mma_commit(&bars[B_EMPTY_B + st]);
       }
     }
   } else if (warp < 2) {
