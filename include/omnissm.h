@@ -244,8 +244,9 @@ OMNI_API int omni_selective_scan_bwd(const omni_selscan_bwd_params_t* p, void* s
 OMNI_API int omni_selftest(const void* Cm, const void* Bm, const void* X, const float* P, const float* Xs,
                            const float* S, float* D1, float* D2, float* D3, float* D4, int which, void* stream);
 
-/* debug: CTA 0 of subsequent tensor-core SSD launches writes clock64() per (chunk, event) into buf[chunks*32]
- * (device int64; NULL disables).  Used by scripts/trace_tc.py to find pipeline stalls. */
+/* debug: CTA 0 of subsequent tensor-core SSD launches writes clock64() per (chunk, event) into buf[n*32]
+ * (device int64; NULL disables) through the TRACE instantiation of the kernel.  `chunks` = 1000 * mode + n: mode 0 the
+ * forward, 1 / 2 the state sweeps of the backward.  Used by scripts/trace_tc.py and scripts/trace_sweep.py. */
 OMNI_API void omni_debug_set_trace(void* buf, int chunks);
 /* debug: as omni_debug_set_trace, for the backward gradient kernel: buf[items * 32] clock64 stamps per phase of CTA 0. */
 OMNI_API void omni_debug_set_bwd_trace(void* buf, int items);
