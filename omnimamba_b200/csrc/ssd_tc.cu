@@ -415,11 +415,13 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         // Yoff = C S16^T  (state entering the chunk); first, so that C(g) is released early (its reload must land before
         // CB(g+1)) - it only needs the state copy and the accumulators the previous epilogue has read
-        wait1(B_S_READY, ph);
+        // (the state copy is the last of the three to arrive: waiting for it last saves two ~100-cycle already-complete
+        // polls between its arrival and the issue, i.e. C(g) is released that much earlier)
         if (g > 0) {
           wait1(B_ACC_FREE + 0, ph ^ 1);
           wait1(B_ACC_FREE + 1, ph ^ 1);
         }
+        wait1(B_S_READY, ph);
         tc_fence_after();
         TR(4);
 #pragma unroll
@@ -905,10 +907,9 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
         if (w == kLeadE) {
           wait1(B_TAB_READY + st, n & 1);
-          if (gg > 0) {
-            if (mode == 0) wait1(B_YOFF_DONE, (gg - 1) & 1);  // Yoff(gg-1) has read the S16 tile
-            wait1(B_U_DONE, (gg - 1) & 1);     // S-update(gg-1) is complete
-          }
+          // (forward: Yoff(gg-1) has read the S16 tile - it was issued before Ydiag(gg-1), whose completion the epilogue of
+          // chunk gg-1 has just waited for)
+          if (gg > 0) wait1(B_U_DONE, (gg - 1) & 1);     // S-update(gg-1) is complete
         }
         named_bar_sync(6, 128);
         const float dch = tab->dchunk[hh];
