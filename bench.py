@@ -345,7 +345,7 @@ def main():
                        "l2": f"inputs+output {tokens * BYTES_FWD / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{how} (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback",
-                         "bytes_per_token": BYTES_FWD, "kernel": "ssd_tc_prep_kernel + ssd_tc_fwd_kernel (one C-ABI call per step)"},
+                         "bytes_per_token": BYTES_FWD, "kernel": "ssd_tc_prep_fast_kernel + ssd_tc_fwd_kernel (one C-ABI call per step)"},
             "fwd_bwd": fb, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
             "clocks": clk.summary(),
         }

@@ -57,7 +57,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src, obj, stale = job
         if not stale:
             return src, 0, ""
-        cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-c", src, "-o", obj]
+        # OMNI_NVCC_EXTRA: extra compile flags for experiment builds (e.g. -DOMNI_TC_VARIANTS)
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *os.environ.get("OMNI_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r.returncode, r.stdout + r.stderr
 

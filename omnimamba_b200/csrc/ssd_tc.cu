@@ -52,7 +52,9 @@ constexpr int HD = 64;     // headdim
 constexpr int NS = 128;    // d_state
 // Warps that watch mbarriers for their role sit on schedulers 2 and 3 (with the TMA / MMA threads); the table warps (0, 1),
 // whose serial dt -> cumsum -> exp chain feeds every chunk, share their schedulers with no spinning warp.
-constexpr int kLeadPX = 2, kLeadE = 3;
+// In the FORWARD the epilogue leader is warp 12 instead (scheduler 0): there scheduler 3 is the busiest one during the P
+// build (quadrant 3 has four of the ten blocks, plus the MMA issuer), which paces the chunk (-0.8 % kernel time).
+constexpr int kLeadPX = 2, kLeadE = 3, kLeadEFwd = 0;
 // (measured: storing y with 16-byte global stores straight from registers instead of the staged TMA stores makes the
 // epilogue AND the concurrent P build slower - 32 scattered rows per store instruction load the LSU: 0.52 vs 0.49 ms)
 constexpr bool kDirectY = false;
@@ -275,6 +277,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     if (++it.c == it.cend) it_set(it, it.u + 1);
   };
   constexpr int mode = MODE;  // (one instantiation per mode: the forward does not carry the sweeps' code and vice versa)
+  constexpr int leadE = MODE == 0 ? kLeadEFwd : kLeadE;
   auto cphys = [&](int c) { return mode == 2 ? nchunks - 1 - c : c; };  // chunk visited at step c of an item
 
   if (warp == 2) {
@@ -660,6 +663,8 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         continue;
       }
+      // (D of this warp's head, for the x pass: issued before the waits so that the load never stalls the pass)
+      const float Dh = a.D ? ld_any(a.D, a.D_dtype, it.h0 + sub) : 0.f;
       if (pw == kLeadPX) {
         wait1(B_TAB_READY + st, n & 1);
         wait1(B_CB_DONE, ph);
@@ -751,7 +756,6 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       named_bar_sync(3, 256);
       if (mode == 0 && g > 0) tc_fence_after();
       const float sji = mode == 2 ? tab->eL[sub][i] : tab->sj[sub][i];  // (reverse sweep: dy rows scale by exp(lam_i))
-      const float Dh = a.D ? ld_any(a.D, a.D_dtype, it.h0 + sub) : 0.f;
       if (xw == 0) TR(17);
       {
         const float2 ss = make_float2(sji, sji), dd = make_float2(Dh, Dh);
@@ -835,7 +839,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const uint32_t st = g & 1, ph = g & 1;
         const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
         const float eL0 = tab->eL[0][r], eL1 = tab->eL[1][r];
-        if (w == kLeadE) wait1(B_YD_DONE, ph);   // Yoff(g) was issued before Ydiag(g): complete as well
+        if (w == leadE) wait1(B_YD_DONE, ph);   // Yoff(g) was issued before Ydiag(g): complete as well
         named_bar_sync(6, 128);
         tc_fence_after();
         if (w == 0) TR(19);
@@ -885,9 +889,11 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                              pack_bf16(y[4 * k + 2].x, y[4 * k + 2].y), pack_bf16(y[4 * k + 3].x, y[4 * k + 3].y));
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0 && ec * Q + w * 32 < a.L) {  // rows beyond L are clipped by the tensor map
-              tma_store_4d(&mapY, slot, 32 * half, eh0 + hx, ec * Q + w * 32, eb);
-              tma_store_commit();
+            if (ec * Q + w * 32 < a.L) {  // (warp-uniform; rows beyond L are clipped by the tensor map)
+              if (elect_one()) {  // elected lane + uniform operands: no R2UR funnel around the store (-1.7 % kernel time)
+                tma_store_4d(&mapY, slot, 32 * half, eh0 + hx, ec * Q + w * 32, eb);
+                tma_store_commit();
+              }
             }
           } else if (t < a.L) {  // fp32 output (parity tests): straight to HBM
             float4* dst = reinterpret_cast<float4*>(static_cast<float*>(a.out) + eb * a.o_b + (int64_t)t * a.o_l +
@@ -905,7 +911,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const uint32_t g = gg;  // (for the trace macro)
         const uint32_t st = gg & 1, n = gg >> 1;
         const Tab* tab = reinterpret_cast<const Tab*>(smem + SM_TAB) + st;
-        if (w == kLeadE) {
+        if (w == leadE) {
           wait1(B_TAB_READY + st, n & 1);
           // (forward: Yoff(gg-1) has read the S16 tile - it was issued before Ydiag(gg-1), whose completion the epilogue of
           // chunk gg-1 has just waited for)
@@ -1050,6 +1056,36 @@ __global__ void __launch_bounds__(256) ssd_tc_prep_kernel(PrepArgs a) {
   }
 }
 
+// Fast pre-pass for the usual layouts (rows a constant pitch apart across batch / token / group: contiguous tensors and
+// slices of zxbcdt or of the conv output): four 16-byte vectors in flight per thread, no divisions.  The bf16 source is
+// read once (evict-first); the fp16 copies stay in L2 for the scan kernel.
+__global__ void __launch_bounds__(256) ssd_tc_prep_fast_kernel(PrepArgs a, int64_t pitch0, int64_t pitch1) {
+  const int which = blockIdx.y;
+  const int64_t nvec = a.rows * (NS / 8), pitch = which == 0 ? pitch0 : pitch1;
+  const __nv_bfloat16* src = which == 0 ? a.src[0] : a.src[1];  // (no dynamic indexing of the parameter struct)
+  __half* dst = which == 0 ? a.dst[0] : a.dst[1];
+  const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  uint4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = base + k * 256;
+    if (i < nvec) v[k] = __ldcs(reinterpret_cast<const uint4*>(src + (i >> 4) * pitch + (i & 15) * 8));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = base + k * 256;
+    if (i < nvec) {
+      uint4 o;
+      o.x = pack_f16_sat(__uint_as_float(v[k].x << 16), __uint_as_float(v[k].x & 0xffff0000u));
+      o.y = pack_f16_sat(__uint_as_float(v[k].y << 16), __uint_as_float(v[k].y & 0xffff0000u));
+      o.z = pack_f16_sat(__uint_as_float(v[k].z << 16), __uint_as_float(v[k].z & 0xffff0000u));
+      o.w = pack_f16_sat(__uint_as_float(v[k].w << 16), __uint_as_float(v[k].w & 0xffff0000u));
+      *reinterpret_cast<uint4*>(dst + i * 8) = o;
+    }
+  }
+}
+static_assert(NS / 8 == 16, "ssd_tc_prep_fast_kernel: 16 vectors per row");
+
 long long* g_trace = nullptr;
 int g_trace_chunks = 0;
 int g_trace_mode = 0;  // which launch mode records (0 forward, 1 / 2 state sweeps)
@@ -1099,6 +1135,18 @@ int ssd_tc_prep(const omni_tensor_t& Bm, const omni_tensor_t& Cm, void* wsB, voi
   pa.s_b[1] = Cm.stride[0]; pa.s_l[1] = Cm.stride[1]; pa.s_g[1] = Cm.stride[2];
   pa.L = (int)L; pa.G = (int)G; pa.rows = rows;
   const int64_t nvec = rows * (NS / 8);
+  // rows of both tensors a constant pitch apart?  (a size-1 dim may carry any stride)
+  auto row_pitch = [&](const omni_tensor_t& t) -> int64_t {
+    const int64_t pitch = G > 1 ? t.stride[2] : t.stride[1];
+    const bool ok = (G == 1 || L == 1 || t.stride[1] == G * t.stride[2]) && (Bsz == 1 || t.stride[0] == L * G * pitch);
+    return ok ? pitch : -1;
+  };
+  const int64_t pB = row_pitch(Bm), pC = row_pitch(Cm);
+  if (pB >= 0 && pC >= 0 && (nvec + 1023) / 1024 < (1ll << 31)) {
+    ssd_tc_prep_fast_kernel<<<dim3((unsigned)((nvec + 1023) / 1024), 2), 256, 0, s>>>(pa, pB, pC);
+    OMNI_CUDA_LAUNCH_CHECK("ssd_tc_prep_fast_kernel");
+    return OMNI_OK;
+  }
   const unsigned gx = (unsigned)std::min<int64_t>((nvec + 255) / 256, (int64_t)sm_count() * 8);
   ssd_tc_prep_kernel<<<dim3(gx, 2), 256, 0, s>>>(pa);
   OMNI_CUDA_LAUNCH_CHECK("ssd_tc_prep_kernel");
