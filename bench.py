@@ -104,6 +104,52 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def gpu_host_locality(index):
+    """NUMA node and local CPUs of GPU `index` (sysfs), and its current PCIe link.  (-1, None, "?") when unknown."""
+    node, cpus, link = -1, None, "?"
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read())
+        cl = open(f"{base}/local_cpulist").read().strip()
+        cpus = set()
+        for part in cl.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        speed = open(f"{base}/current_link_speed").read().strip()
+        width = open(f"{base}/current_link_width").read().strip()
+        link = f"{speed} x{width}"
+    except Exception:
+        pass
+    return node, cpus, link
+
+
+class near_gpu:
+    """Run the enclosed host allocations on the CPUs local to the GPU (first touch puts the pinned pages on its NUMA node,
+    which is what the H2D / D2H legs of the e2e measurement read and write); the affinity is restored on exit."""
+
+    def __init__(self, index):
+        self.node, self.cpus, self.link = gpu_host_locality(index)
+        self.saved = None
+
+    def __enter__(self):
+        try:
+            allowed = os.sched_getaffinity(0)
+            want = (self.cpus or set()) & allowed
+            if self.node >= 0 and want and want != allowed:
+                self.saved = allowed
+                os.sched_setaffinity(0, want)
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *a):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+        return False
+
+
 def time_cuda(fn, steps, warmup, dist_on):
     """W warm-ups, then EXACTLY `steps` calls bracketed by barrier + synchronize; returns seconds (this rank)."""
     for _ in range(warmup):
@@ -223,7 +269,8 @@ def main():
     batch = max(1, TOKENS_PER_GPU // L)
     tokens = batch * L
     host = make_inputs(batch, L, seed=rank)
-    pinned = {k: v.pin_memory() for k, v in host.items()}
+    with near_gpu(local_rank) as loc:
+        pinned = {k: v.pin_memory() for k, v in host.items()}
     dev = {k: v.to(device) for k, v in host.items()}
     out = torch.empty(batch, L, H, P, device=device, dtype=torch.bfloat16)
 
@@ -270,7 +317,10 @@ def main():
     # PCIe link is full duplex and is the bound here (1.1 GB per step against a 0.5 ms kernel).
     big = ("x", "dt", "B", "C")
     nbuf = 2
-    out_host = [torch.empty(batch, L, H, P, dtype=torch.bfloat16).pin_memory() for _ in range(nbuf)]
+    with near_gpu(local_rank):
+        out_host = [torch.empty(batch, L, H, P, dtype=torch.bfloat16).pin_memory() for _ in range(nbuf)]
+        for t in out_host:
+            t.zero_()
     stage = [{k: torch.empty_like(dev[k]) for k in big} for _ in range(nbuf)]
     y_dev = [None] * nbuf
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
@@ -326,7 +376,8 @@ def main():
     h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in big)
     d2h = out_host[0].numel() * out_host[0].element_size()
     e2e = {"value": world * tokens * steps_e / t_e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "note": "copy-in / compute / copy-out streams, 2 buffer sets; PCIe-bound"}
+           "note": "copy-in / compute / copy-out streams, 2 buffer sets; PCIe-bound", "pcie_link": loc.link,
+           "gpu_numa_node": loc.node, "GBps_h2d": h2d * steps_e / t_e / 1e9, "GBps_d2h": d2h * steps_e / t_e / 1e9}
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------------
     cpu = None
