@@ -153,6 +153,38 @@ def test_ssd_tc_matches_recurrent_at_bench_size():
     assert e < 1e-3 and ef < 3e-3
 
 
+@pytest.mark.parametrize("G", [1, 2])
+def test_ssd_tc_prepass_layouts(G):
+    """The fp16 pre-pass of B and C has a division-free path for rows a constant pitch apart (contiguous tensors, channel
+    slices of a wider row such as the conv output) and a generic one for every other stride pattern (here: a batch stride
+    that is not L rows, and B / C interleaved in one buffer).  All layouts must give the bit-identical y and final state."""
+    from omnimamba_b200.interface.ssd_combined import ssd_fwd_raw
+    g = torch.Generator(device=DEV).manual_seed(3)
+    B, L, H, P, N = 3, 391, 8, 64, 128
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g).bfloat16()
+    x, dt, Bm, Cm = rn(B, L, H, P), rn(B, L, H), rn(B, L, G, N), rn(B, L, G, N)
+    A = -(torch.rand(H, device=DEV, generator=g) * 4 + 0.5)
+    dt_bias = torch.rand(H, device=DEV, generator=g) * 4 - 6
+    D = torch.ones(H, device=DEV)
+    run = lambda b, c: ssd_fwd_raw(x, dt, A, b, c, 256, D=D, dt_bias=dt_bias, dt_softplus=True, return_final_states=True,
+                                   algo="chunked_tc")
+    y0, f0 = run(Bm, Cm)
+    # (a) channel slices of one wide row (B, L, 2 G N + 64): constant row pitch when G == 1 -> fast path
+    wide = torch.zeros(B, L, 2 * G * N + 64, device=DEV, dtype=torch.bfloat16)
+    wide[..., :G * N] = Bm.reshape(B, L, G * N)
+    wide[..., G * N:2 * G * N] = Cm.reshape(B, L, G * N)
+    y1, f1 = run(wide[..., :G * N].view(B, L, G, N), wide[..., G * N:2 * G * N].view(B, L, G, N))
+    # (b) padded sequence: batch stride (L + 7) rows -> generic path
+    padB = torch.zeros(B, L + 7, G, N, device=DEV, dtype=torch.bfloat16)
+    padC = torch.zeros(B, L + 7, G, N, device=DEV, dtype=torch.bfloat16)
+    padB[:, :L] = Bm
+    padC[:, :L] = Cm
+    y2, f2 = run(padB[:, :L], padC[:, :L])
+    torch.cuda.synchronize()
+    for y, f in ((y1, f1), (y2, f2)):
+        assert torch.equal(y, y0) and torch.equal(f, f0)
+
+
 @pytest.mark.parametrize("B,L,H", [(5, 633, 64), (3, 300, 128), (10, 129, 32)])
 def test_ssd_tc_half_item_schedule(B, L, H):
     """More items than SMs with a remainder of at most half the grid: the left-over items are cut into two half sequences
