@@ -4,7 +4,7 @@ the image, on the bench workload (B=16, L=4096, H=64, P=64, G=1, N=128, bf16, D,
   vllm       vllm.model_executor.layers.mamba.ops.ssd_combined.mamba_chunk_scan_combined_varlen - the Triton port of
              mamba_ssm's five forward kernels (chunk 256, fp32 states); the stand-in for "the reference mamba-ssm build",
              which cannot be installed here.  Its kernels are autotuned: the first call compiles ~60 configurations.
-  flashinfer flashinfer.mamba.SSDCombined - CuTe-DSL tcgen05 kernel (chunk 128, bf16 states, y in (B, H, P, chunk, Q) layout)
+  flashinfer flashinfer.mamba.SSDCombined - CuTe-DSL tcgen05 kernel (chunk 128, bf16 states; y returned as (B, L, H, P))
 
 Timed like bench.py (5 warm-up + 20 steps, CUDA events).  Prints one JSON line; a comparator that fails to import, compile or
 run is reported with its error instead of a number.   python scripts/bench_comparators.py [vllm] [flashinfer]"""
@@ -49,6 +49,7 @@ def main():
                                out=out)
     res = {"workload": f"B={B} L={L} H={H} P={P} G={G} N={N} bf16", "ours_ms": timed(ours)}
     y_ours = out.clone()
+    print("ours", res["ours_ms"], "ms", file=sys.stderr, flush=True)
 
     if "vllm" in which:
         try:
@@ -86,8 +87,9 @@ def main():
             torch.cuda.synchronize()
             res["flashinfer_compile_s"] = time.time() - t0
             res["flashinfer_ms"] = timed(run)
-            # (B, H, P, chunks, Q) -> (B, L, H, P)
-            res["flashinfer_vs_ours_rel_l2"] = rel_l2(yf.permute(0, 3, 4, 1, 2).reshape(B, L, H, P), y_ours)
+            # (run() returns y as (B, L, H, P): its kernel writes (B, H, P, chunks, Q) and the wrapper copies - that copy and
+            # the Triton chunk-cumsum pre-kernel are part of its public call and of the time above)
+            res["flashinfer_vs_ours_rel_l2"] = rel_l2(yf.reshape(B, L, H, P), y_ours)
         except Exception as e:  # noqa: BLE001
             res["flashinfer_error"] = f"{type(e).__name__}: {e}"[:300]
 
