@@ -73,3 +73,16 @@ def test_two_rank_gloo_matches_single_process():
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
     y_cat = torch.cat([r[2] for r in res], 0)                # no data-path collective: outputs are just the shards
     assert torch.allclose(y_cat, y_ref, rtol=1e-6, atol=1e-6)
+
+
+def test_bench_host_locality_is_harmless_without_a_gpu():
+    """bench.py allocates its pinned e2e buffers on the CPUs local to the GPU.  Without a GPU (or without sysfs PCI data, as in
+    the GPU box's VM) the lookup must report "unknown" and the context manager must leave the CPU affinity untouched."""
+    sys.path.insert(0, ROOT)
+    import bench
+    node, cpus, link = bench.gpu_host_locality(0)
+    assert isinstance(node, int) and isinstance(link, str)
+    before = os.sched_getaffinity(0)
+    with bench.near_gpu(0) as loc:
+        assert loc.node == node
+    assert os.sched_getaffinity(0) == before
