@@ -225,14 +225,31 @@ typedef struct omni_selscan_fwd_params {
 } omni_selscan_fwd_params_t;
 OMNI_API int omni_selective_scan_fwd(const omni_selscan_fwd_params_t* p, void* stream);
 
-/* Backward: du, ddelta like u; dB, dC (B, G, N, L) FP32 zeroed by caller; dz optional;
- * dA_part (B, D, N), dD_part, ddelta_bias_part (B, D) fp32 partials; workspace fp32 (B*D*L). */
+/* Backward [selective_scan_cuda.bwd upstream; SelectiveScanFn.backward]: du like u, ddelta like delta; dB, dC
+ * contiguous (B, G, N, L) FP32, zeroed by the caller (accumulated with atomics over the channels of a group);
+ * dz present iff z is; dA_part (B, D, N), dD_part, ddelta_bias_part (B, D) contiguous fp32 partials (the caller sums
+ * over the batch); workspace: omni_selective_scan_bwd_workspace_elems(...) fp32 values (state checkpoints). */
 typedef struct omni_selscan_bwd_params {
   omni_tensor_t u, delta, A, B, C, D, z, delta_bias, dout;
   omni_tensor_t du, ddelta, dB, dC, dz, dA_part, dD_part, ddelta_bias_part, workspace;
   int32_t delta_softplus;
 } omni_selscan_bwd_params_t;
 OMNI_API int omni_selective_scan_bwd(const omni_selscan_bwd_params_t* p, void* stream);
+OMNI_API int64_t omni_selective_scan_bwd_workspace_elems(int64_t batch, int64_t dim, int64_t seqlen, int64_t dstate);
+
+/* ---- projections ---------------------------------------------------------------------------- */
+/* out (M, N) = a (M, K) b (N, K)^T [+ a2 (M, K2) b2 (N, K2)^T]: bf16 operands, fp32 accumulation, out bf16 or fp32.
+ * Replaces the F.linear calls of Mamba2.forward / mamba_split_conv1d_scan_combined (in_proj, out_proj; cuBLAS upstream)
+ * and their backward GEMMs; the optional second pair is the LoRA branch of the reference's in_proj
+ * (/root/reference/models/stage2/lora.py:263-279) accumulated into the same tile.  a, b: either dim contiguous (an
+ * operand may be passed as a transposed view), the other stride a multiple of 8 elements, 16-byte aligned base; a2 / b2
+ * laid out like a / b; out: contiguous 16-byte aligned rows.  M, N, K need not be tile multiples. */
+typedef struct omni_gemm_params {
+  omni_tensor_t a, b, a2, b2;
+  omni_tensor_t out;
+} omni_gemm_params_t;
+OMNI_API int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream);
+OMNI_API int omni_gemm_bf16_supported(void); /* 1 if the driver exports cuTensorMapEncodeTiled */
 
 /* ---- self test ------------------------------------------------------------------------------ */
 /* Runs the tcgen05 GEMM forms (smem/TMEM operands, K-/MN-major) the chunked SSD kernel is built from on one CTA;
@@ -250,6 +267,9 @@ OMNI_API int omni_selftest(const void* Cm, const void* Bm, const void* X, const 
 OMNI_API void omni_debug_set_trace(void* buf, int chunks);
 /* debug: as omni_debug_set_trace, for the backward gradient kernel: buf[items * 32] clock64 stamps per phase of CTA 0. */
 OMNI_API void omni_debug_set_bwd_trace(void* buf, int items);
+/* debug: hold the hand-off flag of the forward's half-item schedule back by delay_us (tests the consumer's wait; a wait
+ * that times out traps the kernel - the launch fails, nothing stale is consumed); enable = 0 disables that schedule. */
+OMNI_API void omni_debug_set_handoff(unsigned delay_us, int enable);
 /* debug: suspend-time hint (ns) used by the mbarrier waits of the tensor-core SSD kernel (tuning experiments). */
 OMNI_API void omni_debug_set_mbar_hint(unsigned ns);
 /* debug: cycles for `iters` tcgen05.ld (mode 0/2: 4 KB each per warp) or 2x tcgen05.st (mode 1) per warp with nwarps warps

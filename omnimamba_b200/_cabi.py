@@ -97,6 +97,10 @@ class SelScanBwd(C.Structure):
                   "dA_part", "dD_part", "ddelta_bias_part", "workspace") + [("delta_softplus", C.c_int32)]
 
 
+class Gemm(C.Structure):
+    _fields_ = _T("a", "b", "a2", "b2", "out")
+
+
 # entry point -> params struct (every symbol include/omnissm.h declares with a params pointer)
 ENTRY_POINTS = {
     "omni_causal_conv1d_fwd": Conv1dFwd,
@@ -111,9 +115,10 @@ ENTRY_POINTS = {
     "omni_selective_state_update": Ssu,
     "omni_selective_scan_fwd": SelScanFwd,
     "omni_selective_scan_bwd": SelScanBwd,
+    "omni_gemm_bf16": Gemm,
 }
 OTHER_SYMBOLS = ["omni_version", "omni_last_error", "omni_launch_count", "omni_reset_launch_count",
-                 "omni_ssd_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint", "omni_debug_set_bwd_trace"]
+                 "omni_ssd_bwd_workspace_elems", "omni_selective_scan_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint", "omni_debug_set_bwd_trace", "omni_debug_set_handoff", "omni_gemm_bf16_supported"]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libomnissm.so")
 _lib: Optional[C.CDLL] = None
@@ -139,6 +144,8 @@ def lib() -> C.CDLL:
     l.omni_reset_launch_count.restype = None
     l.omni_ssd_bwd_workspace_elems.argtypes = [C.c_int64] * 5
     l.omni_ssd_bwd_workspace_elems.restype = C.c_int64
+    l.omni_selective_scan_bwd_workspace_elems.argtypes = [C.c_int64] * 4
+    l.omni_selective_scan_bwd_workspace_elems.restype = C.c_int64
     l.omni_ssd_bwd_tc_workspace_bytes.argtypes = [C.c_int64] * 6
     l.omni_ssd_bwd_tc_workspace_bytes.restype = C.c_int64
     l.omni_ssd_fwd_workspace_bytes.argtypes = [C.c_int64] * 6
@@ -149,6 +156,9 @@ def lib() -> C.CDLL:
     l.omni_debug_set_trace.restype = None
     l.omni_debug_tmem_bench.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     l.omni_debug_tmem_bench.restype = C.c_int
+    l.omni_gemm_bf16_supported.restype = C.c_int
+    l.omni_debug_set_handoff.argtypes = [C.c_uint, C.c_int]
+    l.omni_debug_set_handoff.restype = None
     _lib = l
     return l
 
@@ -210,3 +220,40 @@ def ssd_bwd_tc_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate) 
 
 def ssd_bwd_workspace_elems(batch, seqlen, nheads, headdim, dstate) -> int:
     return int(lib().omni_ssd_bwd_workspace_elems(batch, seqlen, nheads, headdim, dstate))
+
+
+def selscan_bwd_workspace_elems(batch, dim, seqlen, dstate) -> int:
+    return int(lib().omni_selective_scan_bwd_workspace_elems(batch, dim, seqlen, dstate))
+
+
+def gemm_supported() -> bool:
+    return bool(lib().omni_gemm_bf16_supported())
+
+
+def _gemm_operand_ok(t) -> bool:
+    if t.dim() != 2 or t.dtype != torch.bfloat16 or t.data_ptr() % 16:
+        return False
+    r, c = t.shape
+    if t.stride(1) == 1 and (r == 1 or (t.stride(0) % 8 == 0 and t.stride(0) >= c)):
+        return True
+    return t.stride(0) == 1 and (c == 1 or (t.stride(1) % 8 == 0 and t.stride(1) >= r))
+
+
+def gemm_operands_ok(a, b, a2=None, b2=None) -> bool:
+    """True when the tcgen05 GEMM takes these operands in place (bf16, one contiguous dim, 16-byte aligned rows)."""
+    ok = _gemm_operand_ok(a) and _gemm_operand_ok(b) and a.shape[1] == b.shape[1]
+    if a2 is not None:
+        ok = ok and _gemm_operand_ok(a2) and _gemm_operand_ok(b2) and (a2.stride(1) == 1) == (a.stride(1) == 1) and \
+            (b2.stride(1) == 1) == (b.stride(1) == 1)
+    return ok
+
+
+def gemm(a, b, out_dtype=torch.bfloat16, a2=None, b2=None, out=None):
+    """out (M, N) = a (M, K) @ b (N, K)^T [+ a2 @ b2^T] on the tcgen05 GEMM of libomnissm."""
+    M, N = a.shape[0], b.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    p = Gemm()
+    p.a, p.b, p.a2, p.b2, p.out = tdesc(a), tdesc(b), tdesc(a2), tdesc(b2), tdesc(out)
+    call("omni_gemm_bf16", p, a.device)
+    return out

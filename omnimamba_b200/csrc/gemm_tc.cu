@@ -1,0 +1,306 @@
+// bf16 GEMM on tcgen05 tensor cores for the two projections of the Mamba-2 block (sm_100a).
+//
+//   C[M, N] = A1[M, K1] B1[N, K1]^T  (+ A2[M, K2] B2[N, K2]^T),  bf16 operands, fp32 accumulation in TMEM, bf16 or fp32 C.
+//
+// Replaces the cuBLAS calls behind `in_proj` / `out_proj` (F.linear inside mamba_ssm's Mamba2.forward and
+// mamba_split_conv1d_scan_combined) and their backward GEMMs.  The optional second operand
+// pair is the LoRA branch of the reference's in_proj (/root/reference/models/stage2/lora.py:263-279): with A2 = s (x A^T)
+// (M x r) and B2 = the adapter's up-projection (N x r) the rank-r update rides in the SAME accumulator as x W^T - one pass
+// over the 8512-wide output instead of a GEMM, a skinny GEMM and an elementwise add over (M, 8512).
+//
+// Either operand may be K-major (rows of K contiguous: x, W in the forward) or MN-major (given as its transpose, MN
+// contiguous: W in dgrad, dy^T and x^T in wgrad); the shared-memory descriptors take both, so forward, dgrad and wgrad are
+// one kernel.  Ragged M / N / K are handled by TMA (out-of-bounds elements load as zero, stores are clipped).
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0      TMA producer: 4-stage ring of (A 128 x 64, B 256 x 64) bf16 tiles, 128B swizzle, 48 KB per stage
+//   warp 1      MMA issuer: tcgen05.mma 128 x 256 x 16 (4 per stage), accumulators double-buffered in TMEM (2 x 256 columns)
+//   warps 2-5   epilogue: TMEM -> registers -> bf16 / fp32 -> swizzled 16 KB staging slab -> TMA store (two slabs in flight),
+//               overlapping the main loop of the next tile
+// Tiles are walked in groups of kGroupM row blocks x all column blocks so that the A panel of a group and all of B stay in
+// the 126 MB L2 while 148 CTAs stream through them.
+#include <mutex>
+
+#include "umma.cuh"
+
+namespace omni {
+namespace {
+using namespace umma;
+
+constexpr int BM = 128, BN = 256, BK = 64, kStages = 4, kGroupM = 16;
+constexpr int kGemmThreads = 192;
+constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t SLAB_BYTES = 128 * 128;  // 128 rows x 128 B (64 bf16 or 32 fp32 columns)
+constexpr uint32_t G_EPI = kStages * STAGE_BYTES;
+constexpr uint32_t G_BAR = G_EPI + 2 * SLAB_BYTES;
+enum { GB_FULL = 0, GB_EMPTY = kStages, GB_ACC_FULL = 2 * kStages, GB_ACC_EMPTY = 2 * kStages + 2, GB_COUNT = 2 * kStages + 4 };
+constexpr uint32_t G_TMEMPTR = G_BAR + GB_COUNT * 8;
+constexpr uint32_t G_SMEM = G_TMEMPTR + 16;
+static_assert(G_SMEM <= 232448, "shared memory budget");
+
+struct GemmArgs {
+  int M, N, K1, K2;
+  int a_mn, b_mn;   // 1: the operand is MN-major (its transpose is what lies row-major in memory)
+  int out_f32;
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ bool elect_one_g() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void tile_coords(int t, const GemmArgs& a, int& m0, int& n0) {
+  const int per_group = kGroupM * a.tiles_n;
+  const int g = t / per_group, r = t - g * per_group;
+  const int first_m = g * kGroupM;
+  const int gm = min(kGroupM, a.tiles_m - first_m);
+  m0 = (first_m + r % gm) * BM;
+  n0 = (r / gm) * BN;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
+               const __grid_constant__ CUtensorMap mapC, GemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_BAR);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G_TMEMPTR);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars[GB_FULL + i], 1);
+      mbar_init(&bars[GB_EMPTY + i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[GB_ACC_FULL + i], 1);
+      mbar_init(&bars[GB_ACC_EMPTY + i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB1); tma_prefetch_desc(&mapC);
+    if (a.K2 > 0) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_ptr;
+
+  const int ntiles = a.tiles_m * a.tiles_n;
+  const int nk1 = (a.K1 + BK - 1) / BK, nk2 = (a.K2 + BK - 1) / BK, nk = nk1 + nk2;
+
+  if (warp == 0) {
+    // ============ TMA producer ==========================================================================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int m0, n0;
+        tile_coords(t, a, m0, n0);
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&bars[GB_EMPTY + s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          uint64_t* full = &bars[GB_FULL + s];
+          mbar_expect_tx(full, STAGE_BYTES);
+          const bool second = kt >= nk1;
+          const CUtensorMap* mA = second ? &mapA2 : &mapA1;
+          const CUtensorMap* mB = second ? &mapB2 : &mapB1;
+          const int k0 = (second ? kt - nk1 : kt) * BK;
+          if (!a.a_mn) {
+            tma_load_2d(sa, mA, full, k0, m0);                 // box {64 k, 128 rows}
+          } else {
+            tma_load_2d(sa, mA, full, m0, k0);                 // two boxes {64 m, 64 k rows}
+            tma_load_2d(sa + 8192, mA, full, m0 + 64, k0);
+          }
+          if (!a.b_mn) {
+            tma_load_2d(sb, mB, full, k0, n0);                 // box {64 k, 256 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 8192, mB, full, n0 + 64 * j, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============ MMA issuer (warp-uniform control flow, one elected lane issues) =====================================
+    const bool leader = elect_one_g();
+    const uint32_t idesc = make_idesc(BM, BN, kFmtBF16, kFmtBF16, a.a_mn ? kMajorMN : kMajorK, a.b_mn ? kMajorMN : kMajorK);
+    // K-major tiles advance by 32 B per 16-wide K step; MN-major tiles (64-element blocks 8 KB apart) by 16 rows = 2 KB
+    const uint32_t a_lbo = a.a_mn ? 8192u : 16u, b_lbo = a.b_mn ? 8192u : 16u;
+    const uint32_t a_step = a.a_mn ? 128u : 2u, b_step = a.b_mn ? 128u : 2u;
+    uint32_t it = 0, tile_no = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_no) {
+      const uint32_t buf = tile_no & 1, aph = (tile_no >> 1) & 1;
+      mbar_wait(&bars[GB_ACC_EMPTY + buf], aph ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tb + buf * BN;
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(&bars[GB_FULL + s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t dA = make_sdesc(sa, a_lbo, 1024), dB = make_sdesc(sa + A_BYTES, b_lbo, 1024);
+#pragma unroll
+        for (uint32_t k = 0; k < BK / 16; ++k)
+          if (leader) mma_ss(acc, dA + k * a_step, dB + k * b_step, idesc, (kt | (int)k) != 0);
+        if (leader) mma_commit(&bars[GB_EMPTY + s]);
+        __syncwarp();
+      }
+      if (leader) mma_commit(&bars[GB_ACC_FULL + buf]);
+      __syncwarp();
+    }
+  } else {
+    // ============ epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 = rows of the tile ===============================
+    const int q = warp & 3, row = q * 32 + lane;
+    const bool issuer = warp == 2 && lane == 0;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    uint32_t tile_no = 0, slab_no = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_no) {
+      int m0, n0;
+      tile_coords(t, a, m0, n0);
+      const uint32_t buf = tile_no & 1, aph = (tile_no >> 1) & 1;
+      if (lane == 0) mbar_wait(&bars[GB_ACC_FULL + buf], aph);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t acc = tmem_addr(tb, q * 32, buf * BN);
+      const int ncols = min(BN, a.N - n0);
+      const int slab_cols = a.out_f32 ? 32 : 64;
+      const int nslabs = (ncols + slab_cols - 1) / slab_cols;
+#pragma unroll 1
+      for (int sl = 0; sl < nslabs; ++sl, ++slab_no) {
+        uint8_t* slab = smem + G_EPI + (slab_no & 1) * SLAB_BYTES;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(acc + sl * slab_cols, v0);
+        if (!a.out_f32) tmem_ld32(acc + sl * slab_cols + 32, v1);
+        if (issuer) tma_store_wait_read<1>();   // the store issued two slabs ago has read this buffer
+        tmem_ld_wait();
+        if (sl == nslabs - 1) {                 // accumulator buffer fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[GB_ACC_EMPTY + buf]);
+        }
+        named_bar(1, 128);
+        uint8_t* rowp = slab + row * 128;
+        if (a.out_f32) {
+#pragma unroll
+          for (uint32_t c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(rowp + ((c ^ rsw) << 4)) = make_uint4(v0[4 * c], v0[4 * c + 1], v0[4 * c + 2], v0[4 * c + 3]);
+        } else {
+#pragma unroll
+          for (uint32_t c = 0; c < 4; ++c) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(v0[8 * c + 0]), __uint_as_float(v0[8 * c + 1]));
+            o.y = pack_bf16(__uint_as_float(v0[8 * c + 2]), __uint_as_float(v0[8 * c + 3]));
+            o.z = pack_bf16(__uint_as_float(v0[8 * c + 4]), __uint_as_float(v0[8 * c + 5]));
+            o.w = pack_bf16(__uint_as_float(v0[8 * c + 6]), __uint_as_float(v0[8 * c + 7]));
+            *reinterpret_cast<uint4*>(rowp + ((c ^ rsw) << 4)) = o;
+            o.x = pack_bf16(__uint_as_float(v1[8 * c + 0]), __uint_as_float(v1[8 * c + 1]));
+            o.y = pack_bf16(__uint_as_float(v1[8 * c + 2]), __uint_as_float(v1[8 * c + 3]));
+            o.z = pack_bf16(__uint_as_float(v1[8 * c + 4]), __uint_as_float(v1[8 * c + 5]));
+            o.w = pack_bf16(__uint_as_float(v1[8 * c + 6]), __uint_as_float(v1[8 * c + 7]));
+            *reinterpret_cast<uint4*>(rowp + (((c + 4) ^ rsw) << 4)) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar(2, 128);
+        if (issuer) {
+          tma_store_2d(&mapC, slab, n0 + sl * slab_cols, m0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tb, 512);
+}
+
+// (M, K) operand: which dim is contiguous?  0 = K-major, 1 = MN-major, -1 = neither / misaligned
+int operand_major(const omni_tensor_t& t) {
+  if (!present(t) || t.ndim != 2 || t.dtype != OMNI_BF16 || !aligned16(t.data)) return -1;
+  if (t.stride[1] == 1 && (t.shape[0] == 1 || (t.stride[0] % 8 == 0 && t.stride[0] >= t.shape[1]))) return 0;
+  if (t.stride[0] == 1 && (t.shape[1] == 1 || (t.stride[1] % 8 == 0 && t.stride[1] >= t.shape[0]))) return 1;
+  return -1;
+}
+
+int operand_map(CUtensorMap* m, const omni_tensor_t& t, int major, int rows_box) {
+  // K-major: dims (K, MN), box {64, rows_box};  MN-major: dims (MN, K), box {64, 64}
+  if (major == 0) {
+    const uint64_t dims[2] = {(uint64_t)t.shape[1], (uint64_t)t.shape[0]};
+    const uint64_t str[1] = {(uint64_t)(t.shape[0] > 1 ? t.stride[0] : t.shape[1]) * 2};
+    const uint32_t box[2] = {64, (uint32_t)rows_box};
+    return make_tmap(m, t.data, 2, dims, str, box, OMNI_BF16);
+  }
+  const uint64_t dims[2] = {(uint64_t)t.shape[0], (uint64_t)t.shape[1]};
+  const uint64_t str[1] = {(uint64_t)(t.shape[1] > 1 ? t.stride[1] : t.shape[0]) * 2};
+  const uint32_t box[2] = {64, 64};
+  return make_tmap(m, t.data, 2, dims, str, box, OMNI_BF16);
+}
+
+}  // namespace
+}  // namespace omni
+
+using namespace omni;
+
+extern "C" int omni_gemm_bf16_supported(void) { return get_encode_tiled() != nullptr ? 1 : 0; }
+
+extern "C" int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream) {
+  OMNI_CHECK(p != nullptr, OMNI_BAD_SHAPE, "null params");
+  const omni_tensor_t &A = p->a, &B = p->b, &C = p->out;
+  const int amaj = operand_major(A), bmaj = operand_major(B);
+  OMNI_CHECK(amaj >= 0 && bmaj >= 0, OMNI_BAD_STRIDE,
+             "gemm: a (M, K) and b (N, K) must be bf16, 16-byte aligned, with one contiguous dim and the other stride a multiple of 8");
+  const int64_t M = A.shape[0], K1 = A.shape[1], N = B.shape[0];
+  OMNI_CHECK(B.shape[1] == K1, OMNI_BAD_SHAPE, "gemm: a is (M, K), b must be (N, K)");
+  OMNI_CHECK(present(C) && shape_is(C, 2, M, N) && (C.dtype == OMNI_BF16 || C.dtype == OMNI_F32) && (N <= 1 || C.stride[1] == 1) &&
+                 aligned16(C.data) && (M <= 1 || (C.stride[0] * dtype_size(C.dtype)) % 16 == 0),
+             OMNI_BAD_SHAPE, "gemm: out must be (M, N) bf16 / fp32 with contiguous, 16-byte aligned rows");
+  int64_t K2 = 0;
+  if (present(p->a2) || present(p->b2)) {
+    OMNI_CHECK(operand_major(p->a2) == amaj && operand_major(p->b2) == bmaj, OMNI_BAD_STRIDE,
+               "gemm: the second operand pair must have the layout of the first");
+    K2 = p->a2.shape[1];
+    OMNI_CHECK(p->a2.shape[0] == M && p->b2.shape[0] == N && p->b2.shape[1] == K2, OMNI_BAD_SHAPE, "gemm: a2 (M, K2), b2 (N, K2)");
+  }
+  if (M == 0 || N == 0) return OMNI_OK;
+  OMNI_CHECK(K1 > 0, OMNI_BAD_SHAPE, "gemm: K must be positive");
+  OMNI_CHECK(M < (1ll << 31) && N < (1ll << 31) && K1 < (1ll << 31), OMNI_BAD_SHAPE, "gemm: dims must fit in 31 bits");
+  CUtensorMap mA1, mB1, mA2, mB2, mC;
+  if (int rc = operand_map(&mA1, A, amaj, BM)) return rc;
+  if (int rc = operand_map(&mB1, B, bmaj, BN)) return rc;
+  if (K2 > 0) {
+    if (int rc = operand_map(&mA2, p->a2, amaj, BM)) return rc;
+    if (int rc = operand_map(&mB2, p->b2, bmaj, BN)) return rc;
+  } else {
+    mA2 = mA1; mB2 = mB1;
+  }
+  {
+    const bool f32 = C.dtype == OMNI_F32;
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    const uint64_t str[1] = {(uint64_t)(M > 1 ? C.stride[0] : N) * (f32 ? 4u : 2u)};
+    const uint32_t box[2] = {f32 ? 32u : 64u, 128};
+    if (int rc = make_tmap(&mC, C.data, 2, dims, str, box, C.dtype)) return rc;
+  }
+  GemmArgs a{};
+  a.M = (int)M; a.N = (int)N; a.K1 = (int)K1; a.K2 = (int)K2;
+  a.a_mn = amaj; a.b_mn = bmaj; a.out_f32 = C.dtype == OMNI_F32;
+  a.tiles_m = (int)((M + BM - 1) / BM); a.tiles_n = (int)((N + BN - 1) / BN);
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(once[dev & 63], [] {
+    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+  });
+  const int64_t ntiles = (int64_t)a.tiles_m * a.tiles_n;
+  const int grid = (int)std::min<int64_t>(ntiles, sm_count());
+  gemm_tc_kernel<<<grid, kGemmThreads, G_SMEM, static_cast<cudaStream_t>(stream)>>>(mA1, mB1, mA2, mB2, mC, a);
+  OMNI_CUDA_LAUNCH_CHECK("gemm_tc_kernel");
+  return OMNI_OK;
+}

@@ -126,6 +126,9 @@ struct TcArgs {
     }                                                                                             \
   } while (0)
 
+// debug: microseconds the producer of a half-item hand-off holds its flag back (omni_debug_set_handoff_delay)
+static __device__ uint32_t g_handoff_delay_us = 0;
+
 __device__ __forceinline__ float ex2f(float v) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -825,7 +828,11 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       if (pend == 2) {
         __threadfence();
         named_bar_sync(1, 128);
-        if (r == 0) atomicExch(a.flags + bid, 1);
+        if (r == 0) {
+          // (debug knob: hold the flag back to exercise the consumer's wait, tests/test_gpu_tc.py)
+          for (uint32_t left = g_handoff_delay_us; left > 0; --left) __nanosleep(1000);
+          atomicExch(a.flags + bid, 1);
+        }
       }
       pend = 0;
     };
@@ -931,11 +938,16 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             // second half of a split item: the state after the first half comes from hand-off slot bid - R
             const int slot = bid - R;
             if (r == 0) {
+              // The producer (CTA bid - R) ran its half item FIRST and is co-resident (the host only enables `split` when
+              // the whole grid fits on the device at once), so the flag is normally long set.  The wait is bounded so
+              // that a scheduling surprise cannot hang the GPU - but it never falls through: on a timeout (~4 s) the
+              // kernel traps, the launch fails with a CUDA error and no stale state is ever consumed.
               int ok = 0;
-              for (int spin = 0; spin < (1 << 22) && !ok; ++spin) {  // (bounded: a scheduling bug must not hang the GPU)
+              for (int spin = 0; spin < (1 << 22) && !ok; ++spin) {
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ok) : "l"(a.flags + slot) : "memory");
-                if (!ok) __nanosleep(200);
+                if (!ok) __nanosleep(1000);
               }
+              if (!ok) __trap();
             }
             named_bar_sync(1, 128);
             __threadfence();
@@ -1086,6 +1098,9 @@ __global__ void __launch_bounds__(256) ssd_tc_prep_fast_kernel(PrepArgs a, int64
 }
 static_assert(NS / 8 == 16, "ssd_tc_prep_fast_kernel: 16 vectors per row");
 
+// debug state (omni_debug_set_trace / omni_debug_set_split): plain process globals, read once per launch on the calling
+// thread - set them only while no other thread is launching (the tracing scripts and tests are single-threaded)
+bool g_no_split = false;
 long long* g_trace = nullptr;
 int g_trace_chunks = 0;
 int g_trace_mode = 0;  // which launch mode records (0 forward, 1 / 2 state sweeps)
@@ -1245,6 +1260,17 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   });
   const int nitems = (int)(Bsz * (H / 2));
   const int grid = nitems < sm_count() ? nitems : sm_count();
+  // The half-item schedule makes one CTA wait for another: only legal when every CTA of the grid is resident at once.
+  // (1 CTA per SM by construction; a context with fewer SMs than sm_count() - MPS partitions, green contexts - reports
+  // fewer co-resident blocks here and runs the plain schedule.)
+  static int resident[64];
+  static std::once_flag occ_once[64];
+  std::call_once(occ_once[dev & 63], [dev] {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ssd_tc_fwd_kernel<0, false>, kThreads, SMEM_BYTES) != cudaSuccess) per_sm = 0;
+    resident[dev & 63] = per_sm * sm_count();
+  });
+  if (resident[dev & 63] < grid || g_no_split) { flags = nullptr; a.hand = nullptr; a.flags = nullptr; }
   if (flags != nullptr) {  // hand-off flags of the half-item schedule (a memset node under graph capture)
     if (cudaMemsetAsync(flags, 0, kHandSlots * sizeof(int), s) != cudaSuccess) { flags = nullptr; a.hand = nullptr; a.flags = nullptr; }
   }
@@ -1297,6 +1323,13 @@ int64_t ssd_tc_hand_bytes() { return (int64_t)kHandSlots * (128 * NS * (int64_t)
 
 // debug: suspend-time hint (ns) of the mbarrier waits inside the tensor-core SSD kernel
 extern "C" void omni_debug_set_mbar_hint(unsigned ns) { cudaMemcpyToSymbol(omni::umma::g_mbar_hint_ns, &ns, sizeof(ns)); }
+
+// debug: hold back the hand-off flag of the half-item schedule by `us` microseconds (exercises the consumer's wait);
+// enable = 0 switches the half-item schedule off altogether
+extern "C" void omni_debug_set_handoff(unsigned delay_us, int enable) {
+  cudaMemcpyToSymbol(omni::g_handoff_delay_us, &delay_us, sizeof(delay_us));
+  omni::g_no_split = enable == 0;
+}
 
 // debug: CTA 0 of the next ssd_tc launches records clock64() per (chunk, event) into buf[chunks * 32] (device int64)
 extern "C" void omni_debug_set_trace(void* buf, int chunks) {

@@ -21,6 +21,11 @@ PFN_encodeTiled get_encode_tiled() {
 
 int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, bool is_bf16, int swizzle) {
+  return make_tmap(out, base, rank, dims, strides_bytes, box, is_bf16 ? OMNI_BF16 : OMNI_F16, swizzle);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int dtype, int swizzle) {
   PFN_encodeTiled enc = get_encode_tiled();
   OMNI_CHECK(enc != nullptr, OMNI_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
   OMNI_CHECK(aligned16(base), OMNI_BAD_STRIDE, "TMA: base pointer must be 16-byte aligned");
@@ -36,7 +41,9 @@ int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t
       gstr[i - 1] = strides_bytes[i - 1];
     }
   }
-  CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+  const CUtensorMapDataType ty = dtype == OMNI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : dtype == OMNI_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(out, ty, (cuuint32_t)rank,
                    const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

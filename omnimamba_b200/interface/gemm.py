@@ -1,0 +1,110 @@
+"""in_proj (+LoRA) / out_proj GEMMs of the Mamba-2 block.
+
+`linear(x, w, bias)` is F.linear's contract (y = x w^T + bias) and `lora_linear` the reference's LoRA-wrapped in_proj
+(/root/reference/models/stage2/lora.py:263-279: y = x W^T + B(A(dropout(x))) * alpha / r).  bf16 CUDA operands run on the
+hand-written tcgen05 GEMM of libomnissm (csrc/gemm_tc.cu) - forward, dgrad and wgrad are the same kernel with different
+operand majors; anything else (fp32 parameters outside autocast, CPU tensors in the host-logic tests) goes to torch."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn.functional as F
+
+from .. import _cabi as abi
+
+_BACKEND = os.environ.get("OMNI_GEMM", "tc")  # "tc" (libomnissm tcgen05 kernel) | "torch" (cuBLAS, for A/B comparisons)
+
+
+def _autocast_dtype(device_type="cuda"):
+    return torch.get_autocast_dtype(device_type) if torch.is_autocast_enabled(device_type) else None
+
+
+def gemm_tc_available() -> bool:
+    return _BACKEND == "tc" and hasattr(abi, "gemm") and abi.gemm_supported()
+
+
+def _eligible(*ts):
+    return gemm_tc_available() and all(t.is_cuda and t.dtype == torch.bfloat16 for t in ts)
+
+
+def mm_nt(a, b, out_dtype=None, a2=None, b2=None):
+    """a (M, K) @ b (N, K)^T [+ a2 (M, K2) @ b2 (N, K2)^T] -> (M, N).  Operands may be transposed views (either dim
+    contiguous): the kernel takes K-major and MN-major tiles alike."""
+    od = out_dtype or a.dtype
+    if _eligible(a, b) and abi.gemm_operands_ok(a, b, a2, b2) and (b.shape[0] * (4 if od == torch.float32 else 2)) % 16 == 0 \
+            and od in (torch.bfloat16, torch.float32):
+        return abi.gemm(a, b, od, a2, b2)
+    r = a @ b.t()
+    if a2 is not None:
+        r = r + a2 @ b2.t()
+    return r if out_dtype is None else r.to(out_dtype)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x w^T (+ x2 w2^T) (+ bias); forward, dgrad and wgrad all run on the same GEMM kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, x2=None, w2=None):
+        ctx.save_for_backward(x, w, x2, w2)
+        ctx.has_bias = bias is not None
+        x2f = x2.reshape(-1, x2.shape[-1]) if x2 is not None else None
+        y = mm_nt(x.reshape(-1, x.shape[-1]), w, None, x2f, w2)
+        if bias is not None:
+            y = y + bias
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, x2, w2 = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if dy2.stride(-1) != 1 and dy2.stride(0) != 1:
+            dy2 = dy2.contiguous()
+        need = ctx.needs_input_grad
+        dx = dw = db = dx2 = dw2 = None
+        if need[0]:
+            dx = mm_nt(dy2, w.t()).view(x.shape)                                   # (M, N) @ (N, K)
+        if need[1]:
+            dw = mm_nt(dy2.t(), x.reshape(-1, x.shape[-1]).t())                    # (N, M) @ (M, K)
+        if ctx.has_bias and need[2]:
+            db = dy2.sum(0)
+        if x2 is not None and need[3]:
+            dx2 = mm_nt(dy2, w2.t()).view(x2.shape)
+        if w2 is not None and need[4]:
+            dw2 = mm_nt(dy2.t(), x2.reshape(-1, x2.shape[-1]).t())
+        return dx, dw, db, dx2, dw2
+
+
+def linear(x, w, bias=None):
+    """F.linear with autocast semantics; bf16 CUDA operands run on the tcgen05 GEMM."""
+    ac = _autocast_dtype(x.device.type) if x.is_cuda else None
+    if ac is not None:
+        x, w = x.to(ac), w.to(ac)
+        bias = bias.to(ac) if bias is not None else None
+    if not _eligible(x, w):
+        return F.linear(x, w, bias)
+    with torch.autocast(x.device.type, enabled=False):
+        return _LinearFn.apply(x, w, bias)
+
+
+def lora_linear(x, w, bias, lora_a, lora_b, scaling, dropout=None):
+    """x W^T + (dropout(x) A^T) B^T * scaling  (lora.py:263-279).  The rank-r down projection is a skinny GEMM; the up
+    projection rides in the accumulator of the base GEMM as a second operand pair (A2 = s x A^T, B2 = B)."""
+    xd = dropout(x) if dropout is not None else x
+    ac = _autocast_dtype(x.device.type) if x.is_cuda else None
+    if ac is not None:
+        x, xd, w, lora_a, lora_b = (t.to(ac) for t in (x, xd, w, lora_a, lora_b))
+        bias = bias.to(ac) if bias is not None else None
+    if not _eligible(x, w, lora_a, lora_b):
+        return F.linear(x, w, bias) + F.linear(F.linear(xd, lora_a), lora_b) * scaling
+    with torch.autocast(x.device.type, enabled=False):
+        t = _LinearFn.apply(xd, lora_a, None) * scaling         # (.., r)
+        return _LinearFn.apply(x, w, bias, t, lora_b)
+
+
+class Linear(torch.nn.Linear):
+    """nn.Linear whose forward runs on the tcgen05 GEMM (still an nn.Linear: the reference's LoRA wrapper finds and
+    replaces `in_proj` by isinstance, /root/reference/models/stage2/lora.py:76-106)."""
+
+    def forward(self, x):
+        return linear(x, self.weight, self.bias)

@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from .. import _cabi as abi
 from .causal_conv1d import conv1d_bwd_raw, conv1d_fwd_raw
+from .gemm import mm_nt
 from .layernorm_gated import norm_gated_bwd_raw, norm_gated_fwd_raw
 
 _ALGO = {"auto": abi.SSD_AUTO, "recurrent": abi.SSD_RECURRENT, "chunked_tc": abi.SSD_CHUNKED_TC}
@@ -237,7 +238,9 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
                 y = y.to(ac)
             else:
                 y = y.to(w.dtype)
-            out = F.linear(y, w, b_)
+            out = mm_nt(y.reshape(batch * seqlen, dim), w).view(batch, seqlen, w.shape[0])
+            if b_ is not None:
+                out = out + b_
         else:
             out = y
         ctx.save_for_backward(zxbcdt, conv1d_weight, conv1d_bias, scan_out, A, D, dt_bias, initial_states, seq_idx,
@@ -281,7 +284,9 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
         doutproj_weight = doutproj_bias = drmsnorm_weight = None
         if outproj_weight is not None:
             dout2 = dout.reshape(M, dout.shape[-1])
-            dy = torch.mm(dout2, outproj_weight.to(dout2.dtype))
+            if dout2.stride(-1) != 1 and dout2.stride(0) != 1:
+                dout2 = dout2.contiguous()
+            dy = mm_nt(dout2, outproj_weight.to(dout2.dtype).t())
             doutproj_bias = dout2.sum(0).to(outproj_bias.dtype) if outproj_bias is not None else None
         else:
             dy = dout.reshape(M, dim)
@@ -296,13 +301,13 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
                 dy.to(scan_out.dtype), scan_out.view(M, dim), rmsnorm_weight, None, z2, None, rstd, ctx.rmsnorm_eps,
                 dim // ngroups, ctx.norm_before_gate, True, dx=dscan, dz=dz2, recompute_output=outproj_weight is not None)
             if outproj_weight is not None:
-                doutproj_weight = torch.mm(dout2.t(), y_rec.to(dout2.dtype)).to(outproj_weight.dtype)
+                doutproj_weight = mm_nt(dout2.t(), y_rec.to(dout2.dtype).t()).to(outproj_weight.dtype)
             dscan = dscan.view(batch, seqlen, nheads, headdim)
             zscan, dzscan = None, None
         else:
             if outproj_weight is not None:
                 # y = scan_out (gated inside the scan): the saved tensor is the GEMM input
-                doutproj_weight = torch.mm(dout2.t(), scan_out.view(M, dim).to(dout2.dtype)).to(outproj_weight.dtype)
+                doutproj_weight = mm_nt(dout2.t(), scan_out.view(M, dim).to(dout2.dtype).t()).to(outproj_weight.dtype)
             dscan = dy.to(scan_out.dtype).view(batch, seqlen, nheads, headdim)
             zscan = z.view(batch, seqlen, nheads, headdim)
             dzscan = dz.view(batch, seqlen, nheads, headdim)

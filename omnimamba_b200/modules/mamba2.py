@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..interface.causal_conv1d import causal_conv1d_fn, causal_conv1d_update
+from ..interface.gemm import Linear
 from ..interface.layernorm_gated import RMSNorm as RMSNormGated
 from ..interface.selective_state_update import selective_state_update
 from ..interface.ssd_combined import mamba_chunk_scan_combined, mamba_split_conv1d_scan_combined
@@ -47,7 +48,7 @@ class Mamba2(nn.Module):
 
         # order of the projection: [z, x, B, C, dt]
         d_in_proj = 2 * self.d_inner + 2 * self.ngroups * self.d_state + self.nheads
-        self.in_proj = nn.Linear(self.d_model, d_in_proj, bias=bias, **factory_kwargs)
+        self.in_proj = Linear(self.d_model, d_in_proj, bias=bias, **factory_kwargs)
 
         conv_dim = self.d_ssm + 2 * self.ngroups * self.d_state
         self.conv1d = nn.Conv1d(conv_dim, conv_dim, bias=conv_bias, kernel_size=d_conv, groups=conv_dim,
@@ -75,7 +76,7 @@ class Mamba2(nn.Module):
         if self.rmsnorm:
             self.norm = RMSNormGated(self.d_ssm, eps=1e-5, norm_before_gate=self.norm_before_gate,
                                      group_size=self.d_ssm // ngroups, **factory_kwargs)
-        self.out_proj = nn.Linear(self.d_inner, self.d_model, bias=bias, **factory_kwargs)
+        self.out_proj = Linear(self.d_inner, self.d_model, bias=bias, **factory_kwargs)
 
     # -- helpers -------------------------------------------------------------------------------------------
     def _D(self):

@@ -1,7 +1,7 @@
 """Mamba (v1) mixer with the mamba_ssm==2.2.2 constructor / parameter names (mamba_ssm/modules/mamba_simple.py
 upstream).  Imported by /root/reference/models/stage2/mixer_seq_simple.py:16 and selected only when
-ssm_cfg.layer == "Mamba1" (:197-201) - NOT the OmniMamba default (config_mamba.py:16).  Forward/decode only:
-conv1d + selective_scan_fn run as separate kernels (no fused mamba_inner_fn, no backward)."""
+ssm_cfg.layer == "Mamba1" (:197-201) - NOT the OmniMamba default (config_mamba.py:16).  Trains and decodes:
+with use_fast_path and no cache the block runs through mamba_inner_fn, otherwise conv1d + selective_scan_fn."""
 from __future__ import annotations
 
 import math
@@ -11,7 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..interface.causal_conv1d import causal_conv1d_fn, causal_conv1d_update
-from ..interface.selective_scan import selective_scan_fn
+from ..interface.selective_scan import mamba_inner_fn, selective_scan_fn
 from ..interface.selective_state_update import selective_state_update
 
 
@@ -61,8 +61,12 @@ class Mamba(nn.Module):
                 out, _, _ = self.step(hidden_states, conv_state, ssm_state)
                 return out
         xz = self.in_proj(hidden_states).transpose(1, 2)  # (B, 2*d_inner, L), channel-last
-        x, z = xz.chunk(2, dim=1)
         A = -torch.exp(self.A_log.float())
+        if self.use_fast_path and inference_params is None:
+            return mamba_inner_fn(xz, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
+                                  self.out_proj.weight, self.out_proj.bias, A, None, None, self.D.float(),
+                                  delta_bias=self.dt_proj.bias.float(), delta_softplus=True)
+        x, z = xz.chunk(2, dim=1)
         if conv_state is not None:
             conv_state.copy_(F.pad(x, (self.d_conv - x.shape[-1], 0)))
         x = causal_conv1d_fn(x, self.conv1d.weight.squeeze(1), self.conv1d.bias, activation=self.activation)

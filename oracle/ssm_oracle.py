@@ -32,6 +32,7 @@ __all__ = [
     "mamba2_init_params",
     "mamba2_forward_ref",
     "mamba2_step_ref",
+    "mixer_stack_ref",
     "cpu_recurrent_baseline",
 ]
 
@@ -550,6 +551,28 @@ def mamba2_step_ref(p: Mamba2Params, u: torch.Tensor, conv_state: torch.Tensor, 
     y = rmsnorm_gated_ref(y.reshape(Bsz, p.d_inner), p.norm_weight, None, z=z, eps=p.eps,
                           group_size=p.d_inner // p.ngroups, norm_before_gate=False)
     return F.linear(y, p.out_proj_weight.to(u.dtype)).unsqueeze(1)
+
+
+def mixer_stack_ref(layers, norm_weights, norm_f_weight, hidden_states, eps=1e-5, residual_in_fp32=True,
+                    lora=None, compute_dtype=torch.float32):
+    """The layer loop of MixerModel.forward (/root/reference/models/stage2/mixer_seq_simple.py:404-437) over Block.forward
+    (block.py:86-117, cond=None): per layer `hidden, residual = add_norm(hidden, residual); hidden = mixer(hidden)`, then the
+    final add + norm (prenorm=False).  `layers`: Mamba2Params per layer; `norm_weights[i]`: the layer's RMSNorm weight;
+    `lora`: optional per-layer (A (r, d), B (d_in_proj, r), scaling) added to in_proj as lora.py:263-279 does."""
+    residual = None
+    h = hidden_states
+    for i, p in enumerate(layers):
+        h, residual = layer_norm_ref(h, norm_weights[i], None, residual=residual, eps=eps, prenorm=True,
+                                     residual_in_fp32=residual_in_fp32, is_rms_norm=True)
+        if lora is not None and lora[i] is not None:
+            la, lb, sc = lora[i]
+            q = Mamba2Params.__new__(Mamba2Params)
+            q.__dict__.update(p.__dict__)
+            q.in_proj_weight = p.in_proj_weight + sc * (lb.to(p.in_proj_weight.dtype) @ la.to(p.in_proj_weight.dtype))
+            p = q
+        h = mamba2_forward_ref(p, h, compute_dtype=compute_dtype)
+    return layer_norm_ref(h, norm_f_weight, None, residual=residual, eps=eps, prenorm=False,
+                          residual_in_fp32=residual_in_fp32, is_rms_norm=True)
 
 
 # --------------------------------------------------------------------------- #

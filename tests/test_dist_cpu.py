@@ -86,3 +86,53 @@ def test_bench_host_locality_is_harmless_without_a_gpu():
     with bench.near_gpu(0) as loc:
         assert loc.node == node
     assert os.sched_getaffinity(0) == before
+
+
+def _reducer_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from omnimamba_b200.dist import BucketedGradReducer
+        torch.set_num_threads(1)
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3), torch.nn.Tanh(), torch.nn.Linear(3, 2))
+        net[2].weight.requires_grad_(False)                      # a frozen parameter in the middle (stage "align" pattern)
+        red = BucketedGradReducer(list(net.parameters()), bucket_bytes=40)   # tiny buckets: three of them
+        data = torch.randn(4, 6, generator=torch.Generator().manual_seed(1))
+        out = []
+        for step in range(2):                                    # two steps: zero_grad() must re-arm the buckets
+            red.zero_grad()
+            net(data[rank * 2:(rank + 1) * 2] * (step + 1)).square().mean().backward()
+            red.finish()
+            out.append([p.grad.clone() for p in net.parameters() if p.requires_grad])
+        q.put((rank, out, len(red.buckets), red.total_bytes()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_grad_reducer_two_ranks_equals_full_batch_mean():
+    """DDP semantics: after backward every rank holds the gradient of the mean loss over the GLOBAL batch."""
+    world, port = 2, 31500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_reducer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3), torch.nn.Tanh(), torch.nn.Linear(3, 2))
+    net[2].weight.requires_grad_(False)
+    data = torch.randn(4, 6, generator=torch.Generator().manual_seed(1))
+    for step in range(2):
+        net.zero_grad()
+        net(data * (step + 1)).square().mean().backward()
+        ref = [p.grad for p in net.parameters() if p.requires_grad]
+        for rank, out, nb, nbytes in res:
+            assert nb >= 3 and nbytes == 4 * sum(p.numel() for p in net.parameters() if p.requires_grad)
+            for a, b in zip(out[step], ref):
+                assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)

@@ -1,0 +1,256 @@
+"""Parity at the REAL configurations ("next round" item 1): the bench geometry (d_model=2048: H=64, P=64,
+N=128) against the CPU oracle - not against another kernel of this repo -, the actual training mode (fp32 parameters
+under bf16 autocast, L=329), the 48-layer stack of mixer_seq_simple.py:404-437, and the library kernels in the image
+(vllm's Triton port of the upstream mamba_ssm kernels, flashinfer's SSDCombined) as independent implementations.
+
+Every test prints the PLAIN north-star metric (relative L2 against the fp32 oracle on the same inputs) next to the
+"excess over output rounding" figure of tests/parity_metric.py, so that the two can be read side by side."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from cases import scan_inputs
+from parity_metric import excess_over_rounding, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+H, P, N, G = 64, 64, 128, 1
+bf = lambda t: t.to(torch.bfloat16).float()     # round to bf16, keep computing in fp32 (differentiable: straight through)
+
+
+def _c(t):
+    return None if t is None else t.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (1) the scan at the bench geometry, tensor-core forward AND backward, against the oracle
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L", [329, 4096])
+def test_scan_bench_geometry_vs_oracle(L):
+    """B=1, all 64 heads, L = 329 (stage-1 training length) and 4096 (bench length).  Oracle: fp64 chunked (segsum)
+    evaluation + autograd (identical to the token recurrence, tests/test_oracle.py) on the same bf16-valued inputs."""
+    from omnimamba_b200.interface.ssd_combined import ssd_bwd_raw, ssd_fwd_raw
+    x, dt, A, Bm, Cm, D, dt_bias = scan_inputs(1, L, H, P, G, N, 41, torch.bfloat16)
+    g = torch.Generator().manual_seed(42)
+    dy = torch.randn(1, L, H, P, generator=g).to(torch.bfloat16)
+    leaf = lambda t: t.double().detach().clone().requires_grad_()
+    xr, dtr, Ar, Br, Cr, Dr, dbr = (leaf(t) for t in (x, dt, A, Bm, Cm, D, dt_bias))
+    dtt = oracle.dt_transform(dtr, dbr, True, (0.0, float("inf")))
+    yr, _ = oracle.ssd_chunked_ref(xr, dtt, Ar, Br, Cr, 128, D=Dr, compute_dtype=torch.float64)
+    (yr * dy.double()).sum().backward()
+
+    out32 = torch.empty(1, L, H, P, device=DEV, dtype=torch.float32)
+    ssd_fwd_raw(_c(x), _c(dt), _c(A), _c(Bm), _c(Cm), 256, D=_c(D), dt_bias=_c(dt_bias), dt_softplus=True, out=out32, algo="chunked_tc")
+    out16, _ = ssd_fwd_raw(_c(x), _c(dt), _c(A), _c(Bm), _c(Cm), 256, D=_c(D), dt_bias=_c(dt_bias), dt_softplus=True, algo="chunked_tc")
+    dx, ddt, dA, dB, dC, dD, _, ddtb, _ = ssd_bwd_raw(_c(dy), _c(x), _c(dt), _c(A), _c(Bm), _c(Cm), 256, D=_c(D), dt_bias=_c(dt_bias),
+                                                      dt_softplus=True, algo="chunked_tc")
+    torch.cuda.synchronize()
+    e32, e16, ex16 = rel_l2(out32, yr), rel_l2(out16, yr), excess_over_rounding(out16, yr.float())
+    print(f"scan fwd (1,{L},64,64) tensor-core vs oracle: fp32-out rel_l2 {e32:.2e} | bf16-out rel_l2 {e16:.2e} (excess over rounding {ex16:.2e})")
+    assert e32 <= 5e-4 and ex16 <= 1e-3
+    assert e16 <= 2.5e-3       # = bf16 output rounding (1.5e-3 for an EXACT result) + the kernel's own error
+    assert torch.equal(out16.cpu(), out32.cpu().to(torch.bfloat16))
+    summ = lambda a, ref, terms: ((a.double().cpu() - ref).norm() / terms.norm().clamp_min(1e-30)).item()
+    errs = {"dx": rel_l2(dx, xr.grad), "ddt": rel_l2(ddt, dtr.grad), "dB": rel_l2(dB, Br.grad), "dC": rel_l2(dC, Cr.grad),
+            "dD": rel_l2(dD, Dr.grad), "dA": rel_l2(dA, Ar.grad), "ddt_bias": rel_l2(ddtb, dbr.grad),
+            "dA/|summands|": summ(dA, Ar.grad, dtr.grad / Ar.detach().abs()), "ddt_bias/|summands|": summ(ddtb, dbr.grad, dtr.grad)}
+    print(f"scan bwd (1,{L},64,64) tensor-core vs oracle: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    for k in ("dx", "ddt", "dB", "dC", "dD"):
+        assert errs[k] <= 1e-2, (k, errs[k])
+    for k in ("dA/|summands|", "ddt_bias/|summands|"):
+        assert errs[k] <= 3e-2, (k, errs[k])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (2) the training mode: Mamba2(2048), fp32 parameters, torch.autocast(bfloat16), L = 329, forward + backward
+# ------------------------------------------------------------------------------------------------------------
+def _block_ref_autocast(p, u):
+    """The oracle's Mamba2 forward with the roundings autocast places at op boundaries (GEMM operands and results, conv /
+    scan / norm outputs in bf16; parameters, dt, decay, state and every accumulation in fp32)."""
+    d_inner, conv_dim, nheads = p.d_inner, p.conv_dim, p.nheads
+    zxbcdt = bf(F.linear(bf(u), bf(p.in_proj_weight)))
+    z, xBC, dt = torch.split(zxbcdt, [d_inner, conv_dim, nheads], dim=-1)
+    xBC = bf(oracle.causal_conv1d_ref(xBC.transpose(1, 2), p.conv1d_weight.squeeze(1), p.conv1d_bias, activation="silu").transpose(1, 2))
+    x, Bm, Cm = torch.split(xBC, [d_inner, p.d_state, p.d_state], dim=-1)
+    Bsz, L, _ = u.shape
+    A = -torch.exp(p.A_log.float())
+    y = oracle.mamba_chunk_scan_combined_ref(x.reshape(Bsz, L, nheads, p.headdim), dt, A, Bm.reshape(Bsz, L, 1, -1),
+                                             Cm.reshape(Bsz, L, 1, -1), 256, D=p.D, dt_bias=p.dt_bias, dt_softplus=True)
+    y = bf(y).reshape(Bsz, L, d_inner)
+    y = bf(oracle.rmsnorm_gated_ref(y, p.norm_weight, None, z=z, eps=p.eps, group_size=d_inner, norm_before_gate=False))
+    return bf(F.linear(y, bf(p.out_proj_weight)))
+
+
+def _leafify(p):
+    for k in ("in_proj_weight", "conv1d_weight", "conv1d_bias", "dt_bias", "A_log", "D", "norm_weight", "out_proj_weight"):
+        setattr(p, k, getattr(p, k).detach().clone().float().requires_grad_())
+    return p
+
+
+def _state_dict(p):
+    return {"in_proj.weight": p.in_proj_weight, "conv1d.weight": p.conv1d_weight, "conv1d.bias": p.conv1d_bias,
+            "dt_bias": p.dt_bias, "A_log": p.A_log, "D": p.D, "norm.weight": p.norm_weight, "out_proj.weight": p.out_proj_weight}
+
+
+def test_mamba2_2048_autocast_training_mode():
+    from omnimamba_b200 import _cabi
+    from omnimamba_b200.modules import Mamba2
+    d_model, B, L = 2048, 1, 329
+    p = _leafify(oracle.mamba2_init_params(d_model, seed=3))
+    g = torch.Generator().manual_seed(4)
+    u = torch.randn(B, L, d_model, generator=g)
+    dy = torch.randn(B, L, d_model, generator=g).to(torch.bfloat16)
+    ur = u.clone().requires_grad_()
+    yr = _block_ref_autocast(p, ur)
+    (yr * dy.float()).sum().backward()
+    with torch.no_grad():
+        y_fp32_oracle = oracle.mamba2_forward_ref(p, u)          # no rounding anywhere: the distance autocast itself costs
+
+    m = Mamba2(d_model, layer_idx=0, device=DEV)                 # fp32 parameters
+    m.load_state_dict({k: v.detach().to(DEV) for k, v in _state_dict(p).items()})
+    ug = u.to(DEV).requires_grad_()
+    _cabi.reset_launch_count()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(ug)
+    y.backward(dy.to(DEV))
+    torch.cuda.synchronize()
+    assert y.dtype == torch.bfloat16 and _cabi.launch_count() >= 10
+    e, e0 = rel_l2(y, yr), rel_l2(y, y_fp32_oracle)
+    print(f"Mamba2(2048) autocast bf16 L=329: out rel_l2 {e:.2e} vs boundary-rounded oracle, {e0:.2e} vs unrounded fp32 oracle "
+          f"(the boundary-rounded oracle itself is {rel_l2(yr, y_fp32_oracle):.2e} from the unrounded one)")
+    assert e <= 8e-3, e
+    grads = {"du": (ug.grad, ur.grad)}
+    ref_by_name = {"in_proj.weight": p.in_proj_weight, "conv1d.weight": p.conv1d_weight, "conv1d.bias": p.conv1d_bias, "dt_bias": p.dt_bias,
+                   "A_log": p.A_log, "D": p.D, "norm.weight": p.norm_weight, "out_proj.weight": p.out_proj_weight}
+    for k, prm in m.named_parameters():
+        assert prm.grad is not None and prm.grad.dtype == torch.float32, k
+        grads["d" + k] = (prm.grad, ref_by_name[k].grad)
+    errs = {k: rel_l2(a, b) for k, (a, b) in grads.items()}
+    print("Mamba2(2048) autocast gradients rel_l2: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v <= 3e-2, (k, v)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (3) the layer stack of MixerModel.forward: add+norm -> Mamba2 (LoRA in_proj) x n -> final norm
+# ------------------------------------------------------------------------------------------------------------
+def _stack_case(n_layer, d_model, B, L, seed):
+    from omnimamba_b200.backbone import MixerStack
+    torch.manual_seed(seed)
+    stack = MixerStack(d_model, n_layer, ssm_cfg={})
+    g = torch.Generator().manual_seed(seed + 1)
+    for layer in stack.layers:  # non-trivial norm weights and LoRA adapters (B is zero-initialised)
+        layer.norm.weight.data = torch.rand(d_model, generator=g) + 0.5
+        layer.mixer.in_proj.t2i_lora_B0.weight.data = torch.randn(layer.mixer.in_proj.out_features, 8, generator=g) * 0.02
+        layer.mixer.in_proj.lora_dropout = torch.nn.Identity()
+    stack.norm_f.weight.data = torch.rand(d_model, generator=g) + 0.5
+    x = torch.randn(B, L, d_model, generator=g)
+    layers, norms, lora = [], [], []
+    for layer in stack.layers:
+        m = layer.mixer
+        q = oracle.Mamba2Params(d_model)
+        q.in_proj_weight, q.conv1d_weight, q.conv1d_bias = m.in_proj.weight.data, m.conv1d.weight.data, m.conv1d.bias.data
+        q.dt_bias, q.A_log, q.D, q.norm_weight, q.out_proj_weight = m.dt_bias.data, m.A_log.data, m.D.data, m.norm.weight.data, m.out_proj.weight.data
+        layers.append(q)
+        norms.append(layer.norm.weight.data)
+        lora.append((m.in_proj.t2i_lora_A0.weight.data, m.in_proj.t2i_lora_B0.weight.data, m.in_proj.scaling))
+    with torch.no_grad():
+        ref = oracle.mixer_stack_ref(layers, norms, stack.norm_f.weight.data, x, eps=stack.norm_f.eps, lora=lora)
+    return stack, x, ref
+
+
+@pytest.mark.parametrize("n_layer,d_model,B,L", [(2, 256, 2, 128), (2, 2048, 1, 72), (48, 2048, 1, 40)])
+def test_mixer_stack_vs_oracle_stack(n_layer, d_model, B, L):
+    """fp32 end to end (tolerance 1e-4 after up to 48 layers) and the bf16-autocast run of the same stack, whose distance to
+    the fp32 oracle is recorded (each layer adds a few bf16 roundings to the fp32 residual stream)."""
+    stack, x, ref = _stack_case(n_layer, d_model, B, L, 7)
+    stack = stack.to(DEV)
+    with torch.no_grad():
+        y32 = stack(x.to(DEV))
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y16 = stack(x.to(DEV))
+    torch.cuda.synchronize()
+    e32, e16 = rel_l2(y32, ref), rel_l2(y16, ref)
+    print(f"MixerStack {n_layer} x d_model={d_model} (B={B}, L={L}): fp32 rel_l2 {e32:.2e}; bf16 autocast rel_l2 {e16:.2e}")
+    assert e32 <= 1e-4, e32
+    assert e16 <= 3e-2, e16
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (4) independent implementations in the image
+# ------------------------------------------------------------------------------------------------------------
+def _one_config(kernel):
+    """Pin a Triton autotuner to its first configuration (a parity run does not need the ~60-configuration search)."""
+    if hasattr(kernel, "configs") and len(kernel.configs) > 1:
+        kernel.configs = kernel.configs[:1]
+
+
+def test_scan_vs_vllm_port_of_upstream_kernels():
+    """vllm's Triton port of mamba_ssm v2.2.4's five forward kernels - the closest thing in this image to the reference's own
+    arithmetic (bf16 tl.dot operands, fp32 states, chunk 256).  All three (ours, vllm, oracle) on the same inputs."""
+    try:
+        from vllm.model_executor.layers.mamba.ops import ssd_bmm, ssd_chunk_scan, ssd_chunk_state, ssd_state_passing
+        from vllm.model_executor.layers.mamba.ops.ssd_combined import mamba_chunk_scan_combined_varlen
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"vllm ssd ops not importable: {type(e).__name__}: {e}")
+    for mod, names in ((ssd_bmm, ["_bmm_chunk_fwd_kernel"]), (ssd_chunk_scan, ["_chunk_scan_fwd_kernel"]),
+                       (ssd_chunk_state, ["_chunk_cumsum_fwd_kernel", "_chunk_state_fwd_kernel", "_chunk_state_varlen_kernel"]),
+                       (ssd_state_passing, ["_state_passing_fwd_kernel"])):
+        for nme in names:
+            if hasattr(mod, nme):
+                _one_config(getattr(mod, nme))
+    from omnimamba_b200.interface.ssd_combined import ssd_fwd_raw
+    B, L, Q = 2, 1024, 256
+    x, dt, A, Bm, Cm, D, dt_bias = scan_inputs(B, L, H, P, G, N, 51, torch.bfloat16)
+    ref, fin_ref = oracle.mamba_chunk_scan_combined_ref(x.float(), dt, A, Bm.float(), Cm.float(), Q, D=D, dt_bias=dt_bias, dt_softplus=True,
+                                                        return_final_states=True)
+    ours, fin = ssd_fwd_raw(_c(x), _c(dt), _c(A), _c(Bm), _c(Cm), Q, D=_c(D), dt_bias=_c(dt_bias), dt_softplus=True, return_final_states=True)
+    i32 = dict(device=DEV, dtype=torch.int32)
+    nch = B * L // Q
+    cu_seqlens = torch.arange(0, B * L + 1, L, **i32)
+    cu_chunks = torch.arange(0, B * L + 1, Q, **i32)
+    last_chunk = torch.arange(1, B + 1, **i32) * (L // Q) - 1
+    seq_idx = torch.arange(nch, **i32) // (L // Q)
+    yv = torch.empty(B * L, H, P, device=DEV, dtype=torch.bfloat16)
+    try:
+        states = mamba_chunk_scan_combined_varlen(_c(x).reshape(B * L, H, P), _c(dt).reshape(B * L, H), _c(A), _c(Bm).reshape(B * L, G, N),
+                                                  _c(Cm).reshape(B * L, G, N), Q, cu_seqlens, cu_chunks, last_chunk, seq_idx, yv,
+                                                  D=_c(D), dt_bias=_c(dt_bias), dt_softplus=True, state_dtype=torch.float32)
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"vllm kernel did not run here: {type(e).__name__}: {str(e)[:200]}")
+    torch.cuda.synchronize()
+    yv = yv.view(B, L, H, P)
+    res = {"ours vs oracle": rel_l2(ours, ref), "vllm vs oracle": rel_l2(yv, ref), "ours vs vllm": rel_l2(ours, yv),
+           "ours excess": excess_over_rounding(ours, ref), "vllm excess": excess_over_rounding(yv, ref)}
+    print("scan (2,1024,64,64) bf16: " + ", ".join(f"{k} {v:.2e}" for k, v in res.items()))
+    try:
+        print(f"final states: ours vs oracle {rel_l2(fin, fin_ref):.2e}, vllm vs oracle {rel_l2(states[-B:] if states.shape[0] != B else states, fin_ref):.2e}")
+    except Exception:  # noqa: BLE001  (the varlen call's state layout differs between vllm versions)
+        pass
+    assert res["ours excess"] <= 1e-3
+    assert res["ours vs vllm"] <= 6e-3           # two bf16 outputs: 2 independent roundings (2.2e-3) + upstream's bf16 operand error
+    assert res["ours vs oracle"] <= res["vllm vs oracle"] * 1.05 + 1e-4, "must be at least as close to the oracle as the upstream port"
+
+
+def test_scan_vs_flashinfer_ssd_combined():
+    try:
+        from flashinfer.mamba import SSDCombined
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"flashinfer.mamba not importable: {type(e).__name__}: {e}")
+    from omnimamba_b200.interface.ssd_combined import ssd_fwd_raw
+    B, L = 2, 1024
+    x, dt, A, Bm, Cm, D, dt_bias = scan_inputs(B, L, H, P, G, N, 52, torch.bfloat16)
+    ref = oracle.mamba_chunk_scan_combined_ref(x.float(), dt, A, Bm.float(), Cm.float(), 128, D=D, dt_bias=dt_bias, dt_softplus=True)
+    ours, _ = ssd_fwd_raw(_c(x), _c(dt), _c(A), _c(Bm), _c(Cm), 128, D=_c(D), dt_bias=_c(dt_bias), dt_softplus=True)
+    try:
+        ssd = SSDCombined(chunk_size=128, nheads=H, headdim=P, dstate=N, ngroups=G)
+        yf, _ = ssd.run(_c(x), _c(dt), _c(A), _c(Bm), _c(Cm), D=_c(D).to(torch.bfloat16), dt_bias=_c(dt_bias), dt_softplus=True)
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"flashinfer SSDCombined did not run here: {type(e).__name__}: {str(e)[:200]}")
+    torch.cuda.synchronize()
+    yf = yf.reshape(B, L, H, P)
+    res = {"ours vs oracle": rel_l2(ours, ref), "flashinfer vs oracle": rel_l2(yf, ref), "ours vs flashinfer": rel_l2(ours, yf)}
+    print("scan (2,1024,64,64) bf16: " + ", ".join(f"{k} {v:.2e}" for k, v in res.items()))
+    assert res["ours vs flashinfer"] <= 6e-3
+    assert res["ours vs oracle"] <= res["flashinfer vs oracle"] * 1.05 + 1e-4

@@ -1,0 +1,91 @@
+"""The tcgen05 GEMM behind in_proj / out_proj (csrc/gemm_tc.cu) against a plain PyTorch fp32
+reference of the same op (F.linear on the same bf16-valued operands, fp32 math), through the C-ABI.
+
+Tolerances: fp32 output <= 1e-5 relative L2 (fp32 accumulation of exact bf16 products); bf16 output: the error beyond the
+output rounding itself (tests/parity_metric.py) <= 1e-4, and bit-equality with the rounded fp32 output."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from parity_metric import excess_over_rounding, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16)
+
+
+def _operand(rows, cols, seed, major, pad=0):
+    """(rows, cols) bf16 operand on the device, K-major (cols contiguous, optional row padding) or MN-major (a transposed view)."""
+    t = _rand((rows, cols), seed)
+    if major == "k":
+        buf = torch.zeros(rows, cols + pad, dtype=torch.bfloat16, device=DEV)
+        buf[:, :cols] = t.to(DEV)
+        return t, buf[:, :cols]
+    buf = torch.zeros(cols, rows + pad, dtype=torch.bfloat16, device=DEV)
+    buf[:, :rows] = t.t().to(DEV)
+    return t, buf[:, :rows].t()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 2048), (329, 8512, 2048), (1000, 2048, 4096), (90 * 329, 264, 200),
+                                   (1, 8, 8), (130, 8, 2048), (64, 16384, 2048)])
+@pytest.mark.parametrize("amaj,bmaj", [("k", "k"), ("k", "mn"), ("mn", "mn"), ("mn", "k")])
+def test_gemm_matches_fp32_reference(M, N, K, amaj, bmaj):
+    from omnimamba_b200 import _cabi
+    a, ad = _operand(M, K, 1, amaj, pad=8)
+    b, bd = _operand(N, K, 2, bmaj, pad=16)
+    ref = a.float() @ b.float().t()
+    assert _cabi.gemm_operands_ok(ad, bd)
+    o32 = _cabi.gemm(ad, bd, torch.float32)
+    o16 = _cabi.gemm(ad, bd, torch.bfloat16)
+    torch.cuda.synchronize()
+    e32 = rel_l2(o32, ref)
+    ex = excess_over_rounding(o16, ref)
+    print(f"gemm M={M} N={N} K={K} {amaj}/{bmaj}: fp32-out rel_l2 {e32:.2e}, bf16-out excess {ex:.2e}, plain {rel_l2(o16, ref):.2e}")
+    assert e32 <= 1e-5, e32
+    assert ex <= 1e-4, ex
+    assert torch.equal(o16.cpu(), o32.cpu().to(torch.bfloat16))
+
+
+def test_gemm_second_operand_pair_is_lora():
+    """out = x W^T + t B^T in one accumulator (the LoRA branch of in_proj, lora.py:263-279): d_model=2048 -> 8512, r = 8."""
+    from omnimamba_b200 import _cabi
+    M, K, N, r = 700, 2048, 8512, 8
+    x, w = _rand((M, K), 3), _rand((N, K), 4, 0.02)
+    t, bl = _rand((M, r), 5), _rand((N, r), 6, 0.1)
+    ref = x.float() @ w.float().t() + t.float() @ bl.float().t()
+    out = _cabi.gemm(x.to(DEV), w.to(DEV), torch.float32, t.to(DEV), bl.to(DEV))
+    torch.cuda.synchronize()
+    e = rel_l2(out, ref)
+    print(f"gemm + LoRA pair: {e:.2e}")
+    assert e <= 1e-5, e
+
+
+def test_linear_autograd_matches_torch():
+    """interface.gemm.linear / lora_linear: forward, dgrad, wgrad (all on the tcgen05 kernel) against F.linear in fp32."""
+    from omnimamba_b200.interface.gemm import linear, lora_linear
+    from omnimamba_b200 import _cabi
+    M, K, N, r, s = 2 * 329, 2048, 8512, 8, 4.0
+    x, w = _rand((2, 329, K), 7), _rand((N, K), 8, 0.02)
+    la, lb = _rand((r, K), 9, 0.02), _rand((N, r), 10, 0.05)
+    dy = _rand((2, 329, N), 11)
+    leaves = [t.float().requires_grad_() for t in (x, w, la, lb)]
+    yr = F.linear(leaves[0], leaves[1]) + F.linear(F.linear(leaves[0], leaves[2]), leaves[3]) * s
+    yr.backward(dy.float())
+    d = [t.to(DEV).requires_grad_() for t in (x, w, la, lb)]
+    _cabi.reset_launch_count()
+    y = lora_linear(d[0], d[1], None, d[2], d[3], s)
+    y.backward(dy.to(DEV))
+    torch.cuda.synchronize()
+    assert _cabi.launch_count() >= 6, "forward (2) + backward (>= 4) GEMMs must run on libomnissm"
+    # the rank-r intermediate t = s x A^T is rounded to bf16 before the up-projection (as under autocast upstream)
+    assert excess_over_rounding(y, yr) <= 2e-3
+    for name, a, b in zip(("dx", "dW", "dA", "dB"), d, leaves):
+        e = excess_over_rounding(a.grad, b.grad)
+        print(f"lora_linear {name}: excess {e:.2e} plain {rel_l2(a.grad, b.grad):.2e}")
+        assert e <= 5e-3, (name, e)
+    y2 = linear(d[0].detach(), d[1].detach())
+    assert excess_over_rounding(y2, F.linear(x.float(), w.float())) <= 1e-4
