@@ -229,6 +229,9 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "recurrent", "chunked_tc"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-bwd", action="store_true", help="skip the fwd+bwd leg")
+    ap.add_argument("--workloads", default="model_fwd,train,decode",
+                    help="whole-model legs reported under \"workloads\" (BASELINE configs 2, 3, 4; bench_workloads.py); \"none\" skips them")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the back-to-back loop behind roofline.sustained")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -291,6 +294,16 @@ def main():
     # call is charged to the roofline (conservative)
     kernel_s = t_fwd / args.steps
     achieved = tokens * BYTES_FWD / kernel_s / 1e9
+
+    # ---- sustained: the same call back to back for >= 2 s (power-limited clocks), beside the 20-step burst ---------
+    sustained = None
+    if args.sustained_s > 0:
+        n_sus = max(args.steps, int(args.sustained_s / kernel_s) + 1)
+        with ClockSampler(local_rank) as clk_s:
+            t_sus = max_over_ranks(time_cuda(fwd, n_sus, 1, dist_on), dist_on, device)
+        ach_s = tokens * BYTES_FWD * n_sus / t_sus / 1e9
+        sustained = {"steps": n_sus, "seconds": t_sus, "ms_per_step": 1e3 * t_sus / n_sus, "value": world * tokens * n_sus / t_sus,
+                     "achieved": ach_s, "frac": ach_s / hbm, "sm_mhz": clk_s.summary()["sm_mhz"]}
 
     # ---- fwd + bwd -----------------------------------------------------------------------------------------
     fb = None
@@ -385,6 +398,15 @@ def main():
         tps, cores, sample, _, _ = cpu_arm()
         cpu = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
 
+    # ---- whole-model workloads (configs 2, 3, 4): their own numbers, never folded into `value` ----------------
+    wl = None
+    if args.workloads != "none":
+        import bench_workloads
+        del stage, y_dev, out_host
+        torch.cuda.empty_cache()
+        which = [w for w in args.workloads.split(",") if w]
+        wl = bench_workloads.run_all(device, rank, world, which, hbm)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -396,8 +418,9 @@ def main():
                        "l2": f"inputs+output {tokens * BYTES_FWD / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{how} (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback",
-                         "bytes_per_token": BYTES_FWD, "kernel": "ssd_tc_prep_fast_kernel + ssd_tc_fwd_kernel (one C-ABI call per step)"},
-            "fwd_bwd": fb, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
+                         "bytes_per_token": BYTES_FWD, "kernel": "ssd_tc_prep_fast_kernel + ssd_tc_fwd_kernel (one C-ABI call per step)",
+                         "sustained": sustained},
+            "fwd_bwd": fb, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "workloads": wl,
             "clocks": clk.summary(),
         }
         print(json.dumps(line), flush=True)

@@ -27,13 +27,16 @@ namespace omni {
 namespace {
 using namespace umma;
 
-constexpr int BM = 128, BN = 256, BK = 64, kStages = 4, kGroupM = 16;
+// Two tile shapes: 128 x 256 (4 stages) for the training / prefill GEMMs, 128 x 64 (8 stages) when there are too few
+// 256-wide column blocks to occupy the machine (decode: M = batch <= 128 rows, the weights stream once).
+constexpr int BM = 128, BK = 64, kGroupM = 16;
 constexpr int kGemmThreads = 192;
-constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t A_BYTES = BM * BK * 2;
 constexpr uint32_t SLAB_BYTES = 128 * 128;  // 128 rows x 128 B (64 bf16 or 32 fp32 columns)
-constexpr uint32_t G_EPI = kStages * STAGE_BYTES;
+constexpr uint32_t G_EPI = 4 * (A_BYTES + 256 * BK * 2);   // = 8 * (A_BYTES + 64 * BK * 2): both shapes use 192 KB of stages
 constexpr uint32_t G_BAR = G_EPI + 2 * SLAB_BYTES;
-enum { GB_FULL = 0, GB_EMPTY = kStages, GB_ACC_FULL = 2 * kStages, GB_ACC_EMPTY = 2 * kStages + 2, GB_COUNT = 2 * kStages + 4 };
+constexpr int kMaxStages = 8;
+enum { GB_FULL = 0, GB_EMPTY = kMaxStages, GB_ACC_FULL = 2 * kMaxStages, GB_ACC_EMPTY = 2 * kMaxStages + 2, GB_COUNT = 2 * kMaxStages + 4 };
 constexpr uint32_t G_TMEMPTR = G_BAR + GB_COUNT * 8;
 constexpr uint32_t G_SMEM = G_TMEMPTR + 16;
 static_assert(G_SMEM <= 232448, "shared memory budget");
@@ -52,6 +55,7 @@ __device__ __forceinline__ bool elect_one_g() {
 }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+template <int BN>
 __device__ __forceinline__ void tile_coords(int t, const GemmArgs& a, int& m0, int& n0) {
   const int per_group = kGroupM * a.tiles_n;
   const int g = t / per_group, r = t - g * per_group;
@@ -61,10 +65,14 @@ __device__ __forceinline__ void tile_coords(int t, const GemmArgs& a, int& m0, i
   n0 = (r / gm) * BN;
 }
 
+template <int BN, int kStages>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
                const __grid_constant__ CUtensorMap mapC, GemmArgs a) {
+  constexpr uint32_t B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t kTmemCols = 2 * BN;
+  static_assert(kStages * STAGE_BYTES <= G_EPI && kStages <= kMaxStages, "stage ring");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_BAR);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G_TMEMPTR);
@@ -81,7 +89,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB1); tma_prefetch_desc(&mapC);
     if (a.K2 > 0) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
@@ -100,7 +108,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       uint32_t it = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int m0, n0;
-        tile_coords(t, a, m0, n0);
+        tile_coords<BN>(t, a, m0, n0);
         for (int kt = 0; kt < nk; ++kt, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(&bars[GB_EMPTY + s], ph ^ 1);
@@ -119,10 +127,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
             tma_load_2d(sa + 8192, mA, full, m0 + 64, k0);
           }
           if (!a.b_mn) {
-            tma_load_2d(sb, mB, full, k0, n0);                 // box {64 k, 256 rows}
+            tma_load_2d(sb, mB, full, k0, n0);                 // box {64 k, BN rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 8192, mB, full, n0 + 64 * j, k0);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, mB, full, n0 + 64 * j, k0);
           }
         }
       }
@@ -163,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
     uint32_t tile_no = 0, slab_no = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_no) {
       int m0, n0;
-      tile_coords(t, a, m0, n0);
+      tile_coords<BN>(t, a, m0, n0);
       const uint32_t buf = tile_no & 1, aph = (tile_no >> 1) & 1;
       if (lane == 0) mbar_wait(&bars[GB_ACC_FULL + buf], aph);
       __syncwarp();
@@ -219,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tb, 512);
+  if (warp == 1) tmem_dealloc(tb, kTmemCols);
 }
 
 // (M, K) operand: which dim is contiguous?  0 = K-major, 1 = MN-major, -1 = neither / misaligned
@@ -272,6 +280,10 @@ extern "C" int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream) {
   if (M == 0 || N == 0) return OMNI_OK;
   OMNI_CHECK(K1 > 0, OMNI_BAD_SHAPE, "gemm: K must be positive");
   OMNI_CHECK(M < (1ll << 31) && N < (1ll << 31) && K1 < (1ll << 31), OMNI_BAD_SHAPE, "gemm: dims must fit in 31 bits");
+  // too few 128 x 256 tiles to occupy the SMs (decode: M = batch): 128 x 64 tiles, four times as many CTAs stream the weights
+  const int64_t tiles_m = (M + BM - 1) / BM;
+  const bool narrow = tiles_m * ((N + 255) / 256) * 2 <= sm_count() && N > 64;
+  const int BN = narrow ? 64 : 256;
   CUtensorMap mA1, mB1, mA2, mB2, mC;
   if (int rc = operand_map(&mA1, A, amaj, BM)) return rc;
   if (int rc = operand_map(&mB1, B, bmaj, BN)) return rc;
@@ -291,16 +303,19 @@ extern "C" int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream) {
   GemmArgs a{};
   a.M = (int)M; a.N = (int)N; a.K1 = (int)K1; a.K2 = (int)K2;
   a.a_mn = amaj; a.b_mn = bmaj; a.out_f32 = C.dtype == OMNI_F32;
-  a.tiles_m = (int)((M + BM - 1) / BM); a.tiles_n = (int)((N + BN - 1) / BN);
+  a.tiles_m = (int)tiles_m; a.tiles_n = (int)((N + BN - 1) / BN);
   static std::once_flag once[64];
   int dev = 0;
   cudaGetDevice(&dev);
   std::call_once(once[dev & 63], [] {
-    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    cudaFuncSetAttribute(gemm_tc_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    cudaFuncSetAttribute(gemm_tc_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
   });
   const int64_t ntiles = (int64_t)a.tiles_m * a.tiles_n;
   const int grid = (int)std::min<int64_t>(ntiles, sm_count());
-  gemm_tc_kernel<<<grid, kGemmThreads, G_SMEM, static_cast<cudaStream_t>(stream)>>>(mA1, mB1, mA2, mB2, mC, a);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (narrow) gemm_tc_kernel<64, 8><<<grid, kGemmThreads, G_SMEM, s>>>(mA1, mB1, mA2, mB2, mC, a);
+  else gemm_tc_kernel<256, 4><<<grid, kGemmThreads, G_SMEM, s>>>(mA1, mB1, mA2, mB2, mC, a);
   OMNI_CUDA_LAUNCH_CHECK("gemm_tc_kernel");
   return OMNI_OK;
 }

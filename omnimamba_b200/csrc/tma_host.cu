@@ -29,6 +29,17 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
   PFN_encodeTiled enc = get_encode_tiled();
   OMNI_CHECK(enc != nullptr, OMNI_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
   OMNI_CHECK(aligned16(base), OMNI_BAD_STRIDE, "TMA: base pointer must be 16-byte aligned");
+  // The encode is a DRIVER call and needs a current context on the calling thread.  PyTorch's autograd worker threads only
+  // record their device (no context is bound until the first runtime call), so bind the primary context of the thread's
+  // current device once per (thread, device) - otherwise a backward that starts with a tensor-map encode fails with 201.
+  {
+    static thread_local int bound_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != bound_dev) {
+      cudaSetDevice(dev);
+      bound_dev = dev;
+    }
+  }
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {

@@ -21,6 +21,7 @@ def _rand(shape, seed, scale=1.0):
 def _operand(rows, cols, seed, major, pad=0):
     """(rows, cols) bf16 operand on the device, K-major (cols contiguous, optional row padding) or MN-major (a transposed view)."""
     t = _rand((rows, cols), seed)
+    pad += (-(rows if major == "mn" else cols) - pad) % 8   # row pitch stays a multiple of 8 elements (16 bytes)
     if major == "k":
         buf = torch.zeros(rows, cols + pad, dtype=torch.bfloat16, device=DEV)
         buf[:, :cols] = t.to(DEV)
