@@ -268,8 +268,9 @@ OMNI_API void omni_debug_set_trace(void* buf, int chunks);
 /* debug: as omni_debug_set_trace, for the backward gradient kernel: buf[items * 32] clock64 stamps per phase of CTA 0. */
 OMNI_API void omni_debug_set_bwd_trace(void* buf, int items);
 /* debug: hold the hand-off flag of the forward's half-item schedule back by delay_us (tests the consumer's wait; a wait
- * that times out traps the kernel - the launch fails, nothing stale is consumed); enable = 0 disables that schedule. */
-OMNI_API void omni_debug_set_handoff(unsigned delay_us, int enable);
+ * that times out traps the kernel - the launch fails, nothing stale is consumed); `schedules` (default 3): bit 0 enables
+ * the half-item hand-off schedule, bit 1 the piece schedule (few long sequences cut into independent pieces). */
+OMNI_API void omni_debug_set_handoff(unsigned delay_us, int schedules);
 /* debug: suspend-time hint (ns) used by the mbarrier waits of the tensor-core SSD kernel (tuning experiments). */
 OMNI_API void omni_debug_set_mbar_hint(unsigned ns);
 /* debug: cycles for `iters` tcgen05.ld (mode 0/2: 4 KB each per warp) or 2x tcgen05.st (mode 1) per warp with nwarps warps

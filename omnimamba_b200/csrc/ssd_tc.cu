@@ -114,6 +114,7 @@ struct TcArgs {
   // ENTERING every chunk (for the backward): 1 = forward states S_c from (x, B, sj); 2 = reverse sweep of the state
   // gradient dS_{c+1} from (dy in the x slot, C in the B slot, exp(lam_i) as the row scale), chunks visited last to first.
   int mode;
+  int no_store;  // modes 1 / 2: do not store the per-chunk states (only the final state is wanted: piece schedule)
 };
 
 // trace slot layout: trace[g * 32 + event]
@@ -1020,15 +1021,15 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         __syncwarp();
         if (w == 0) TR(16);
         if (lane == 0) mbar_arrive(&bars[B_S_READY]);
-        if (mode != 0) {  // state sweeps: the state ENTERING this chunk -> workspace[b][chunk][(h,p)][n] (fp16), no epilogue
+        if (mode != 0 && !a.no_store) {  // state sweeps: the state ENTERING this chunk -> workspace[b][chunk][(h,p)][n] (fp16)
           named_bar_sync(1, 128);
           if (w == 0 && lane == 0) {
             tma_store_4d(&mapS, smem + SM_S, 0, sn.h0 * HD, cphys(sn.c), sn.b);
             tma_store_4d(&mapS, smem + SM_S + 16384, 64, sn.h0 * HD, cphys(sn.c), sn.b);
             tma_store_commit();
           }
-          if (lane == 0) mbar_arrive(&bars[B_TAB_FREE + st]);
         }
+        if (mode != 0 && lane == 0) mbar_arrive(&bars[B_TAB_FREE + st]);
         it_next(sn);
       }
     }
@@ -1101,6 +1102,62 @@ static_assert(NS / 8 == 16, "ssd_tc_prep_fast_kernel: 16 vectors per row");
 // debug state (omni_debug_set_trace / omni_debug_set_split): plain process globals, read once per launch on the calling
 // thread - set them only while no other thread is launching (the tracing scripts and tests are single-threaded)
 bool g_no_split = false;
+// ---- piece schedule (few long sequences: B H / 2 work items cannot fill 148 SMs) ---------------------------------------
+// Every sequence is cut into k equal pieces that run as independent sequences: (1) a state sweep (mode 1, no stores) gives
+// the state each piece would END with from a zero start, (2) ssd_piece_decay_kernel the total decay exp(sum dt A) of each
+// piece, (3) ssd_piece_combine_kernel chains them, S_enter(p) = decay(p-1) S_enter(p-1) + S_local(p-1), and (4) the forward
+// runs on the pieces with S_enter as their initial states.  Costs one extra sweep (~0.55 of a forward) for k-fold parallelism.
+struct PieceArgs {
+  const void* dt; const float* A; const void* dt_bias;
+  int64_t dt_b, dt_l, dt_h;
+  int Bk, Lp, H;          // pieces (B * k), tokens per piece, heads
+  int dt_dtype, dtb_dtype, dt_softplus;
+  float dt_min, dt_max;
+  float* decay;           // [Bk][H]
+};
+__global__ void __launch_bounds__(256) ssd_piece_decay_kernel(PieceArgs a) {
+  const int h = blockIdx.x, bp = blockIdx.y;
+  const float bias = a.dt_bias ? ld_any(a.dt_bias, a.dtb_dtype, h) : 0.f;
+  float sum = 0.f;
+  for (int t = threadIdx.x; t < a.Lp; t += blockDim.x) {
+    float v = ld_any(a.dt, a.dt_dtype, (int64_t)bp * a.dt_b + (int64_t)t * a.dt_l + (int64_t)h * a.dt_h) + bias;
+    if (a.dt_softplus) v = softplus_fast(v);
+    sum += fminf(fmaxf(v, a.dt_min), a.dt_max);
+  }
+  __shared__ float red[32];
+  sum = block_sum(sum, red);
+  if (threadIdx.x == 0) a.decay[(int64_t)bp * a.H + h] = __expf(sum * a.A[h]);
+}
+struct CombineArgs {
+  const void* init; int init_dtype; int64_t i_b, i_h, i_p;
+  const float* local;     // [B * k][H][64][128] state each piece ends with from a zero start
+  const float* decay;     // [B * k][H]
+  float* enter;           // [B * k][H][64][128] state each piece starts from
+  int B, k, H;
+};
+__global__ void __launch_bounds__(256) ssd_piece_combine_kernel(CombineArgs a) {
+  const int64_t per = (int64_t)a.H * HD * NS, total = (int64_t)a.B * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per);
+    const int64_t r = i - b * per;
+    const int h = (int)(r / (HD * NS)), pn = (int)(r - (int64_t)h * HD * NS), pp = pn / NS, n = pn - pp * NS;
+    float S = a.init ? ld_any(a.init, a.init_dtype, b * a.i_b + (int64_t)h * a.i_h + (int64_t)pp * a.i_p + n) : 0.f;
+    for (int p = 0; p < a.k; ++p) {
+      const int64_t o = ((int64_t)(b * a.k + p)) * per + r;
+      a.enter[o] = S;
+      if (p + 1 < a.k) S = a.decay[(int64_t)(b * a.k + p) * a.H + h] * S + a.local[o];
+    }
+  }
+}
+__global__ void __launch_bounds__(256) ssd_piece_final_kernel(const float* piece_fin, float* fin, int B, int k, int64_t per) {
+  const int64_t total = (int64_t)B * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per;
+    fin[i] = piece_fin[(b * k + (k - 1)) * per + (i - b * per)];
+  }
+}
+bool g_no_pieces = false;  // debug (omni_debug_set_handoff): plain schedule only
+
 long long* g_trace = nullptr;
 int g_trace_chunks = 0;
 int g_trace_mode = 0;  // which launch mode records (0 forward, 1 / 2 state sweeps)
@@ -1173,7 +1230,7 @@ namespace {
 int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const omni_tensor_t& A, const omni_tensor_t& D,
               const omni_tensor_t& dt_bias, const omni_tensor_t& init, const omni_tensor_t& fin, const omni_tensor_t& o,
               const void* wsB, const void* wsC, void* ws_states, int64_t G, int dt_softplus, float dt_min, float dt_max,
-              cudaStream_t s, float* hand = nullptr, int* flags = nullptr) {
+              cudaStream_t s, float* hand = nullptr, int* flags = nullptr, bool no_store = false) {
   const int64_t Bsz = x.shape[0], L = x.shape[1], H = x.shape[2];
   const int64_t nchunks = (L + Q - 1) / Q;
   OMNI_CHECK(present(dt) && shape_is(dt, 3, Bsz, L, H) && is_float_dtype(dt.dtype), OMNI_BAD_SHAPE, "ssd: dt must be (B, L, H)");
@@ -1214,6 +1271,7 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   a.dt_softplus = dt_softplus; a.dt_min = dt_min; a.dt_max = dt_max;
   a.trace = mode == g_trace_mode ? g_trace : nullptr; a.trace_chunks = g_trace_chunks;
   a.hand = hand; a.flags = flags;
+  a.no_store = no_store ? 1 : 0;
 
   auto tmap4 = [&](CUtensorMap* m, const void* base, const int64_t* shape, const int64_t* stride, bool bf16, int rows) -> int {
     // dims innermost first: (inner, dim2, L, B); a size-1 dim may carry any stride: give TMA a harmless legal one
@@ -1238,7 +1296,7 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   } else {
     mY = mX;  // unused
   }
-  if (mode != 0) {  // fp16 states: (n 128, rows H*64, chunk, batch), box 64 x 128 rows
+  if (mode != 0 && !no_store) {  // fp16 states: (n 128, rows H*64, chunk, batch), box 64 x 128 rows
     const uint64_t dims[4] = {(uint64_t)NS, (uint64_t)(H * HD), (uint64_t)nchunks, (uint64_t)Bsz};
     const uint64_t strides[3] = {(uint64_t)NS * 2, (uint64_t)(H * HD * NS) * 2, (uint64_t)(nchunks * H * HD * NS) * 2};
     const uint32_t box[4] = {64, 128, 1, 1};
@@ -1286,6 +1344,33 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
 }
 }  // namespace
 
+namespace {
+// pieces per sequence of the piece schedule (1 = plain schedule)
+int piece_count(int64_t Bsz, int64_t L, int64_t H) {
+  const int64_t items = Bsz * (H / 2), sm = sm_count();
+  if (g_no_pieces || items <= 0 || items * 2 > sm) return 1;
+  int64_t k = sm / items;
+  if (k > 16) k = 16;
+  while (k > 1 && (L % k != 0 || L / k < 8 * Q)) --k;
+  return (int)k;
+}
+int64_t piece_ws_bytes(int64_t Bsz, int64_t L, int64_t H) {
+  const int k = piece_count(Bsz, L, H);
+  if (k <= 1) return 0;
+  return 3 * Bsz * k * H * HD * NS * (int64_t)sizeof(float) + Bsz * k * H * (int64_t)sizeof(float) + 1024;
+}
+// (B, L, ...) -> (B k, L / k, ...): a view, when the batch stride is L rows
+bool piece_view(const omni_tensor_t& t, int k, omni_tensor_t& v) {
+  v = t;
+  if (!present(t)) return true;
+  if (t.shape[0] > 1 && t.stride[0] != t.shape[1] * t.stride[1]) return false;
+  v.shape[0] = t.shape[0] * k;
+  v.shape[1] = t.shape[1] / k;
+  v.stride[0] = v.shape[1] * t.stride[1];
+  return true;
+}
+}  // namespace
+
 int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
   const omni_tensor_t &x = p->x, &Bm = p->B, &Cm = p->C, &o = p->out;
   const int64_t Bsz = x.shape[0], L = x.shape[1], H = x.shape[2], G = Bm.shape[2];
@@ -1299,6 +1384,66 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
   tail += (256 - reinterpret_cast<uintptr_t>(tail) % 256) % 256;
   float* hand = reinterpret_cast<float*>(tail);
   int* flags = reinterpret_cast<int*>(tail + (size_t)kHandSlots * 128 * NS * sizeof(float));
+
+  // ---- piece schedule: too few (batch, head pair) items for the SMs -> cut every sequence into k independent pieces ----
+  int k = piece_count(Bsz, L, H);
+  omni_tensor_t xv, dtv, ov;
+  if (k > 1 && !(piece_view(x, k, xv) && piece_view(p->dt, k, dtv) && piece_view(o, k, ov))) k = 1;
+  if (k > 1) {
+    const int64_t Bk = Bsz * k, per = H * HD * NS;
+    char* pw = reinterpret_cast<char*>(flags + kHandSlots);
+    pw += (256 - reinterpret_cast<uintptr_t>(pw) % 256) % 256;
+    float* local = reinterpret_cast<float*>(pw);
+    float* enter = local + Bk * per;
+    float* pfin = enter + Bk * per;
+    float* decay = pfin + Bk * per;
+    omni_tensor_t none{};
+    auto state_tensor = [&](float* ptr) {
+      omni_tensor_t t{};
+      t.data = ptr; t.dtype = OMNI_F32; t.ndim = 4;
+      t.shape[0] = Bk; t.shape[1] = H; t.shape[2] = HD; t.shape[3] = NS;
+      t.stride[3] = 1; t.stride[2] = NS; t.stride[1] = HD * NS; t.stride[0] = per;
+      return t;
+    };
+    const omni_tensor_t t_local = state_tensor(local), t_enter = state_tensor(enter), t_pfin = state_tensor(pfin);
+    // (1) state each piece ends with from a zero start: the state sweep of the backward, without its per-chunk stores
+    if (int rc = tc_launch(1, xv, dtv, p->A, none, p->dt_bias, none, t_local, none, wsB, nullptr, nullptr, G, p->dt_softplus,
+                           p->dt_min, p->dt_max, s, hand, flags, true))
+      return rc;
+    // (2) total decay of every piece, (3) the chain over the pieces of a sequence
+    PieceArgs pa{};
+    pa.dt = dtv.data; pa.A = static_cast<const float*>(p->A.data); pa.dt_bias = p->dt_bias.data;
+    pa.dt_b = dtv.stride[0]; pa.dt_l = dtv.stride[1]; pa.dt_h = dtv.stride[2];
+    pa.Bk = (int)Bk; pa.Lp = (int)(L / k); pa.H = (int)H;
+    pa.dt_dtype = dtv.dtype; pa.dtb_dtype = p->dt_bias.dtype; pa.dt_softplus = p->dt_softplus;
+    pa.dt_min = p->dt_min; pa.dt_max = p->dt_max; pa.decay = decay;
+    ssd_piece_decay_kernel<<<dim3((unsigned)H, (unsigned)Bk), 256, 0, s>>>(pa);
+    OMNI_CUDA_LAUNCH_CHECK("ssd_piece_decay_kernel");
+    CombineArgs ca{};
+    if (present(p->initial_states)) {
+      const omni_tensor_t& in = p->initial_states;
+      OMNI_CHECK(shape_is(in, 4, Bsz, H, HD, NS) && is_float_dtype(in.dtype) && in.stride[3] == 1, OMNI_BAD_SHAPE,
+                 "ssd: initial_states must be (B, H, P, N)");
+      ca.init = in.data; ca.init_dtype = in.dtype; ca.i_b = in.stride[0]; ca.i_h = in.stride[1]; ca.i_p = in.stride[2];
+    }
+    ca.local = local; ca.decay = decay; ca.enter = enter; ca.B = (int)Bsz; ca.k = k; ca.H = (int)H;
+    ssd_piece_combine_kernel<<<sm_count() * 4, 256, 0, s>>>(ca);
+    OMNI_CUDA_LAUNCH_CHECK("ssd_piece_combine_kernel");
+    // (4) the forward over the pieces, each from the state it enters with
+    const bool want_fin = present(p->final_states);
+    if (int rc = tc_launch(0, xv, dtv, p->A, p->D, p->dt_bias, t_enter, want_fin ? t_pfin : none, ov, wsB, wsC, nullptr, G,
+                           p->dt_softplus, p->dt_min, p->dt_max, s, hand, flags))
+      return rc;
+    if (want_fin) {
+      const omni_tensor_t& fin = p->final_states;
+      OMNI_CHECK(shape_is(fin, 4, Bsz, H, HD, NS) && fin.dtype == OMNI_F32 && fin.stride[3] == 1 && fin.stride[2] == NS &&
+                     fin.stride[1] == HD * NS && fin.stride[0] == per,
+                 OMNI_BAD_SHAPE, "ssd: final_states must be contiguous fp32 (B, H, P, N)");
+      ssd_piece_final_kernel<<<sm_count() * 2, 256, 0, s>>>(pfin, static_cast<float*>(fin.data), (int)Bsz, k, per);
+      OMNI_CUDA_LAUNCH_CHECK("ssd_piece_final_kernel");
+    }
+    return OMNI_OK;
+  }
   return tc_launch(0, x, p->dt, p->A, p->D, p->dt_bias, p->initial_states, p->final_states, o, wsB, wsC, nullptr, G,
                    p->dt_softplus, p->dt_min, p->dt_max, s, hand, flags);
 }
@@ -1325,10 +1470,11 @@ int64_t ssd_tc_hand_bytes() { return (int64_t)kHandSlots * (128 * NS * (int64_t)
 extern "C" void omni_debug_set_mbar_hint(unsigned ns) { cudaMemcpyToSymbol(omni::umma::g_mbar_hint_ns, &ns, sizeof(ns)); }
 
 // debug: hold back the hand-off flag of the half-item schedule by `us` microseconds (exercises the consumer's wait);
-// enable = 0 switches the half-item schedule off altogether
-extern "C" void omni_debug_set_handoff(unsigned delay_us, int enable) {
+// `schedules` switches the work schedules on (default 3): bit 0 half-item hand-off, bit 1 piece schedule
+extern "C" void omni_debug_set_handoff(unsigned delay_us, int schedules) {
   cudaMemcpyToSymbol(omni::g_handoff_delay_us, &delay_us, sizeof(delay_us));
-  omni::g_no_split = enable == 0;
+  omni::g_no_split = (schedules & 1) == 0;    // bit 0: half-item hand-off schedule
+  omni::g_no_pieces = (schedules & 2) == 0;   // bit 1: piece schedule (few long sequences)
 }
 
 // debug: CTA 0 of the next ssd_tc launches records clock64() per (chunk, event) into buf[chunks * 32] (device int64)
@@ -1342,6 +1488,8 @@ extern "C" void omni_debug_set_trace(void* buf, int chunks) {
 extern "C" int64_t omni_ssd_fwd_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim, int64_t ngroups,
                                                 int64_t dstate) {
   (void)nheads; (void)headdim;
-  // fp16 copies of B and C + the hand-off slots (fp32 state of a head pair) and flags of the half-item schedule
-  return 2 * batch * seqlen * ngroups * dstate * 2 + 256 + (int64_t)omni::kHandSlots * (128 * 128 * 4 + 4);
+  // fp16 copies of B and C + the hand-off slots (fp32 state of a head pair) and flags of the half-item schedule + the
+  // per-piece states of the piece schedule (few long sequences)
+  return 2 * batch * seqlen * ngroups * dstate * 2 + 256 + (int64_t)omni::kHandSlots * (128 * 128 * 4 + 4) + 256 +
+         omni::piece_ws_bytes(batch, seqlen, nheads);
 }

@@ -210,6 +210,71 @@ def test_ssd_tc_half_item_schedule(B, L, H):
     assert torch.equal(o2, o3) and torch.equal(f2, f3)
 
 
+def test_ssd_tc_half_item_handoff_waits_for_a_late_producer():
+    """The consumer of a half-item hand-off must WAIT for the producer's flag: the producer is held back by 2 ms
+    (debug knob) and the result must still be bit-identical to the undelayed run; with the schedule switched off the
+    plain schedule gives the same y as well."""
+    from omnimamba_b200 import _cabi
+    from omnimamba_b200.interface.ssd_combined import ssd_fwd_raw
+    lib = _cabi.lib()
+    g = torch.Generator(device=DEV).manual_seed(77)
+    B, L, H, P, N = 5, 633, 64, 64, 128
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g).bfloat16()
+    x, dt, Bm, Cm = rn(B, L, H, P), rn(B, L, H), rn(B, L, 1, N), rn(B, L, 1, N)
+    A = -(torch.rand(H, device=DEV, generator=g) * 15 + 1)
+    dt_bias = torch.rand(H, device=DEV, generator=g) * 4 - 6
+    D = torch.ones(H, device=DEV)
+    run = lambda: ssd_fwd_raw(x, dt, A, Bm, Cm, 256, D=D, dt_bias=dt_bias, dt_softplus=True, return_final_states=True, algo="chunked_tc")
+    y0, f0 = run()
+    try:
+        lib.omni_debug_set_handoff(2000, 3)
+        y1, f1 = run()
+        lib.omni_debug_set_handoff(0, 0)
+        y2, f2 = run()
+        torch.cuda.synchronize()
+    finally:
+        lib.omni_debug_set_handoff(0, 3)
+    assert torch.equal(y0, y1) and torch.equal(f0, f1)
+    assert torch.equal(y0, y2) and rel_l2(f2, f0) < 1e-6
+
+
+@pytest.mark.parametrize("B,L,H,with_init", [(1, 8192, 8, True), (2, 4096, 4, False), (1, 16384, 64, True), (3, 3072, 2, True)])
+def test_ssd_tc_piece_schedule(B, L, H, with_init):
+    """Few (batch, head pair) items: every sequence is cut into k independent pieces (state sweep from a zero start, total
+    decay per piece, chain over the pieces, forward per piece from its entering state).  Must agree with the plain schedule
+    of the same kernel (fp16 state copies differ per chunk start, so not bit-for-bit) and with the exact fp32 SIMT recurrence;
+    final states included."""
+    from omnimamba_b200 import _cabi
+    from omnimamba_b200.interface.ssd_combined import ssd_fwd_raw
+    lib = _cabi.lib()
+    g = torch.Generator(device=DEV).manual_seed(B * L + H)
+    P, N = 64, 128
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g).bfloat16()
+    x, dt, Bm, Cm = rn(B, L, H, P), rn(B, L, H), rn(B, L, 1, N), rn(B, L, 1, N)
+    A = -(torch.rand(H, device=DEV, generator=g) * 15 + 1)
+    A[0] = -0.01   # a head that barely decays: the entering state matters over the whole piece
+    dt_bias = torch.rand(H, device=DEV, generator=g) * 4 - 6
+    D = torch.ones(H, device=DEV)
+    init = torch.randn(B, H, P, N, device=DEV, generator=g) if with_init else None
+    kw = dict(D=D, dt_bias=dt_bias, dt_softplus=True, initial_states=init, return_final_states=True)
+    y_p, f_p = ssd_fwd_raw(x, dt, A, Bm, Cm, 256, algo="chunked_tc", **kw)
+    o32 = torch.empty(B, L, H, P, device=DEV, dtype=torch.float32)
+    ssd_fwd_raw(x, dt, A, Bm, Cm, 256, algo="chunked_tc", out=o32, **kw)
+    try:
+        lib.omni_debug_set_handoff(0, 1)           # piece schedule off
+        y_s, f_s = ssd_fwd_raw(x, dt, A, Bm, Cm, 256, algo="chunked_tc", **kw)
+    finally:
+        lib.omni_debug_set_handoff(0, 3)
+    y_r = torch.empty(B, L, H, P, device=DEV, dtype=torch.float32)
+    _, f_r = ssd_fwd_raw(x.float(), dt.float(), A, Bm.float(), Cm.float(), 256, algo="recurrent", out=y_r, **kw)
+    torch.cuda.synchronize()
+    e_plain, e_rec, e_fin = rel_l2(y_p, y_s), rel_l2(o32, y_r), rel_l2(f_p, f_r)
+    print(f"piece schedule B={B} L={L} H={H}: vs plain schedule {e_plain:.2e}; fp32-out vs fp32 recurrence {e_rec:.2e}; final {e_fin:.2e}")
+    assert e_plain < 2.5e-3      # two bf16 outputs of the same fp32 result up to the kernel's own 2e-4
+    assert e_rec < 5e-4 and e_fin < 3e-3
+    assert rel_l2(f_p, f_s) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------------------------
 # tensor-core chunked SSD backward (state sweeps + per-chunk gradient kernel) vs the oracle's autograd
 # ------------------------------------------------------------------------------------------------------------
