@@ -251,6 +251,19 @@ typedef struct omni_gemm_params {
 OMNI_API int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream);
 OMNI_API int omni_gemm_bf16_supported(void); /* 1 if the driver exports cuTensorMapEncodeTiled */
 
+/* ---- head loss ------------------------------------------------------------------------------ */
+/* Softmax cross-entropy over a block of fp32 logits (the img_head / lm_head GEMM output of omni_gemm_bf16) - the loss
+ * nn.CrossEntropyLoss computes at /root/reference/models/omnimamba.py:276-279 on the shifted logits of
+ * models/mamba_vlm.py:96-100.  fwd: lse[r] = logsumexp(logits[r]), loss[r] = lse[r] - logits[r, labels[r]] (0 where
+ * labels[r] == ignore_index).  bwd: grad[r, v] = (exp(logits[r, v] - lse[r]) - [v == labels[r]]) * scale[0], bf16 (zero rows
+ * where ignored); scale is a DEVICE fp32 scalar (dloss / number of valid labels).  logits (M, V) fp32, labels (M) int64. */
+typedef struct omni_softmax_ce_params {
+  omni_tensor_t logits, labels, lse, loss, scale, grad;
+  int64_t ignore_index;
+} omni_softmax_ce_params_t;
+OMNI_API int omni_softmax_ce_fwd(const omni_softmax_ce_params_t* p, void* stream);
+OMNI_API int omni_softmax_ce_bwd(const omni_softmax_ce_params_t* p, void* stream);
+
 /* ---- self test ------------------------------------------------------------------------------ */
 /* Runs the tcgen05 GEMM forms (smem/TMEM operands, K-/MN-major) the chunked SSD kernel is built from on one CTA;
  * tests/test_gpu_tc.py checks the results.  Cm, Bm: 16-bit [128][128]; X: 16-bit [128][64] (bf16, or fp16 when bit8 of

@@ -101,6 +101,10 @@ class Gemm(C.Structure):
     _fields_ = _T("a", "b", "a2", "b2", "out")
 
 
+class SoftmaxCe(C.Structure):
+    _fields_ = _T("logits", "labels", "lse", "loss", "scale", "grad") + [("ignore_index", C.c_int64)]
+
+
 # entry point -> params struct (every symbol include/omnissm.h declares with a params pointer)
 ENTRY_POINTS = {
     "omni_causal_conv1d_fwd": Conv1dFwd,
@@ -116,6 +120,8 @@ ENTRY_POINTS = {
     "omni_selective_scan_fwd": SelScanFwd,
     "omni_selective_scan_bwd": SelScanBwd,
     "omni_gemm_bf16": Gemm,
+    "omni_softmax_ce_fwd": SoftmaxCe,
+    "omni_softmax_ce_bwd": SoftmaxCe,
 }
 OTHER_SYMBOLS = ["omni_version", "omni_last_error", "omni_launch_count", "omni_reset_launch_count",
                  "omni_ssd_bwd_workspace_elems", "omni_selective_scan_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint", "omni_debug_set_bwd_trace", "omni_debug_set_handoff", "omni_gemm_bf16_supported"]

@@ -66,7 +66,7 @@ struct BTab {
 };
 static_assert(sizeof(BTab) % 16 == 0, "BTab alignment");
 constexpr uint32_t SM_BAR = SM_TAB + sizeof(BTab);
-enum { BB_TMA = 0, BB_C1, BB_C2, BB_C3, BB_C4, BB_C5, BB_C6, BB_COUNT };
+enum { BB_TMA = 0, BB_C1, BB_C2, BB_C3, BB_C4, BB_C5, BB_C6, BB_C8, BB_COUNT };
 constexpr uint32_t SM_TMEMPTR = SM_BAR + BB_COUNT * 8;
 constexpr uint32_t SMEM_BYTES = SM_TMEMPTR + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -220,13 +220,23 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   int it_count = 0;
   bool fresh = true;  // R2 / R3 hold nothing yet for the current group
   // raw dt of (head tid >> 7, token tid & 127) of an item, for the table threads; loaded one item ahead
-  auto load_dt = [&](int item_) -> float {
-    if (tid >= 256 || item_ >= item_hi) return 0.f;
+  // (raw bits: converting at the load site makes the thread - and through the phase barrier every warp - wait ~1000 cycles
+  // for the strided gather right there; measured with the phase trace)
+  auto load_dt = [&](int item_) -> uint32_t {
+    if (tid >= 256 || item_ >= item_hi) return 0u;
     const int hp_ = item_ % HP, bc_ = item_ / HP, c_ = bc_ % a.nchunks, b_ = bc_ / a.nchunks;
     const int t_ = c_ * Q + (tid & 127), h_ = hp_ * 2 + ((tid >> 7) & 1);
-    return t_ < a.L ? ld_any(a.dt, a.dt_dtype, b_ * a.dt_b + (int64_t)t_ * a.dt_l + (int64_t)h_ * a.dt_h) : 0.f;
+    if (t_ >= a.L) return 0u;
+    const int64_t off = b_ * a.dt_b + (int64_t)t_ * a.dt_l + (int64_t)h_ * a.dt_h;
+    return a.dt_dtype == OMNI_F32 ? __ldg(static_cast<const uint32_t*>(a.dt) + off)
+                                  : (uint32_t)__ldg(static_cast<const unsigned short*>(a.dt) + off);
   };
-  float dt_next = load_dt(item_lo);
+  auto dt_to_f = [&](uint32_t bits) -> float {
+    if (a.dt_dtype == OMNI_F32) return __uint_as_float(bits);
+    if (a.dt_dtype == OMNI_BF16) return __uint_as_float(bits << 16);
+    return __half2float(__ushort_as_half((unsigned short)bits));
+  };
+  uint32_t dt_next = load_dt(item_lo);
 #pragma unroll 1
   for (int item = item_lo; item < item_hi; ++item, ph ^= 1, ++it_count) {
     const int hp = item % HP, bc = item / HP, c = bc % a.nchunks, b = bc / a.nchunks;
@@ -256,7 +266,7 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const int t = t0 + tj, h = h0 + th;
       float vpre = 0.f;
       if (t < a.L) {
-        vpre = dt_next;
+        vpre = dt_to_f(dt_next);
         if (a.dt_bias) vpre += ld_any(a.dt_bias, a.dtb_dtype, h);
         float v = a.dt_softplus ? softplus_fast(vpre) : vpre;
         my_dt = fminf(fmaxf(v, a.dt_min), a.dt_max);
@@ -545,6 +555,25 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     BTR(12);
     tc_fence_after();
     dot_c_acc(tab->rr[1]);  // base + (M_0 + M_1) B: both heads' within-chunk parts
+    {  // zc_h = <dS_{c+1}, S_c> over the head's 64 rows: the two fp16 tiles share their (swizzled) layout, so it is an
+       // elementwise product of equal offsets - 32 values per thread (it used to be the trace of a 128 x 128 x 128 GEMM)
+      const uint4* st = reinterpret_cast<const uint4*>(smem + SM_S);
+      const uint4* dst = reinterpret_cast<const uint4*>(smem + SM_DS);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int slot = warp * 128 + k * 32 + lane;      // 16-byte slot; row = (slot >> 3) & 127: a warp stays inside one head
+        const uint4 sv = st[slot], dv = dst[slot];
+        const uint32_t sw4[4] = {sv.x, sv.y, sv.z, sv.w}, dw4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a2 = h2f2(sw4[e]), b2 = h2f2(dw4[e]);
+          acc += a2.x * b2.x + a2.y * b2.y;
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) atomicAdd(&tab->zc[(warp >> 2) & 1], acc);   // slots [warp * 128, +128): rows 16 (warp & 7) .. +15 of n-half warp >> 3
+    }
     {
       uint4* xt = reinterpret_cast<uint4*>(smem + SM_X);
 #pragma unroll 2
@@ -563,22 +592,20 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     tc_fence_before();
     __syncthreads();
     BTR(13);
-    // ---- M. G6: dC += (exp(lam) dy) S_c -> R2;  G8: dB += X' dS_{c+1} -> R3;  G10: C S16^T -> R0;  G11: dS16 S16^T -> R1 ----
+    // ---- M. G10: C S16^T -> R0;  then G6: dC += (exp(lam) dy) S_c -> R2;  G8: dB += X' dS_{c+1} -> R3 ----
     if (tid == 0) {
       tc_fence_after();
       const uint32_t id_kmn = make_idesc(128, 128, kFmtF16, kFmtF16, kMajorK, kMajorMN);
 #pragma unroll
-      for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R2, dDYk + koff(k), dSm + k * 128, id_kmn, true);
-#pragma unroll
-      for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R3, dXk + koff(k), dDSm + k * 128, id_kmn, true);
-#pragma unroll
-      for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R0, dCk + koff(k), dSk + koff(k), id_kk, k > 0);    // G10
-#pragma unroll
-      for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R1, dDSk + koff(k), dSk + koff(k), id_kk, k > 0);   // G11
+      for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R0, dCk + koff(k), dSk + koff(k), id_kk, k > 0);    // G10 first: roff waits for it
       mma_commit(&bars[BB_C6]);
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R2, dDYk + koff(k), dSm + k * 128, id_kmn, true);   // G6, G8 only feed the accumulators:
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k) mma_ss(tb + R3, dXk + koff(k), dDSm + k * 128, id_kmn, true);   // they run under roff / da / ddt
+      mma_commit(&bars[BB_C8]);
     }
-    // ---- N0. roff_i = (exp(lam_i) dy_i) . (C_i S_c): rows i, this warp's 32 columns (h, p) of G10;
-    //          zc_h = <dS_{c+1}, S_c> = the trace of G11 over the head's 64 rows ------------------------------------------
+    // ---- N0. roff_i = (exp(lam_i) dy_i) . (C_i S_c): rows i, this warp's 32 columns (h, p) of G10 ---------------------------
     mbar_wait(&bars[BB_C6], ph);
     BTR(14);
     tc_fence_after();
@@ -601,16 +628,6 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
       }
       atomicAdd(&tab->roff[wq >> 1][row], part);
-      if (wq == 0) {  // diagonal element (row, row) of G11: the lane-th of this warp's 32 diagonal-block columns
-        uint32_t dg[32];
-        tmem_ld32(tmem_addr(tb, q * 32, R1 + 32 * q), dg);
-        tmem_ld_wait();
-        float d = 0.f;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) d = e == lane ? __uint_as_float(dg[e]) : d;
-        const float zs = warp_sum(d);
-        if (lane == 0) atomicAdd(&tab->zc[q >> 1], zs);
-      }
     }
     tc_fence_before();
     __syncthreads();
@@ -667,6 +684,8 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
     BTR(15);
     fresh = false;
+    mbar_wait(&bars[BB_C8], ph);   // G6 / G8 have read the S / dS / x / dy tiles (next item's loads) and completed dC / dB (flush)
+    tc_fence_after();
     // ---- N2. end of a (batch, chunk) group: dC (R2), dB (R3): TMEM -> fp32 staging over the dead x/dy and B/C tiles ->
     //          coalesced vector reductions ----------------------------------------------------------------------------------
     if (last_of_group) {

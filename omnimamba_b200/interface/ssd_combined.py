@@ -2,7 +2,8 @@
 (mamba_ssm/ops/triton/ssd_combined.py upstream; Mamba2.forward paths A and B).
 
 Both are autograd Functions over libomnissm.so entry points.  Everything that touches (B, L, ...)
-activations is one of our CUDA kernels; the only library call is the plain out_proj GEMM (F.linear)."""
+activations is one of our CUDA kernels, the out_proj GEMM and its backward included (interface/gemm.py: the tcgen05 GEMM
+of libomnissm for bf16 operands)."""
 from __future__ import annotations
 
 import math
@@ -299,13 +300,13 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
             dscan = torch.empty(M, dim, device=dev, dtype=scan_out.dtype)
             _, drmsnorm_weight, _, _, y_rec = norm_gated_bwd_raw(
                 dy.to(scan_out.dtype), scan_out.view(M, dim), rmsnorm_weight, None, z2, None, rstd, ctx.rmsnorm_eps,
-                dim // ngroups, ctx.norm_before_gate, True, dx=dscan, dz=dz2, recompute_output=outproj_weight is not None)
-            if outproj_weight is not None:
+                dim // ngroups, ctx.norm_before_gate, True, dx=dscan, dz=dz2, recompute_output=outproj_weight is not None and ctx.needs_input_grad[14])
+            if outproj_weight is not None and ctx.needs_input_grad[14]:   # (frozen out_proj - stage "align" - skips its wgrad)
                 doutproj_weight = mm_nt(dout2.t(), y_rec.to(dout2.dtype).t()).to(outproj_weight.dtype)
             dscan = dscan.view(batch, seqlen, nheads, headdim)
             zscan, dzscan = None, None
         else:
-            if outproj_weight is not None:
+            if outproj_weight is not None and ctx.needs_input_grad[14]:
                 # y = scan_out (gated inside the scan): the saved tensor is the GEMM input
                 doutproj_weight = mm_nt(dout2.t(), scan_out.view(M, dim).to(dout2.dtype).t()).to(outproj_weight.dtype)
             dscan = dy.to(scan_out.dtype).view(batch, seqlen, nheads, headdim)

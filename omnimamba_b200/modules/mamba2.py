@@ -79,6 +79,18 @@ class Mamba2(nn.Module):
         self.out_proj = Linear(self.d_inner, self.d_model, bias=bias, **factory_kwargs)
 
     # -- helpers -------------------------------------------------------------------------------------------
+    def _A(self):
+        """A = -exp(A_log) in fp32.  Outside autograd (decode, prefill) it is cached per version of A_log: recomputing it is
+        three elementwise launches per layer and step inside the captured decode graph (144 of ~430 launches at 48 layers)."""
+        if torch.is_grad_enabled() and self.A_log.requires_grad:
+            return -torch.exp(self.A_log.float())
+        c = getattr(self, "_A_cache", None)
+        if c is None or c[0] != self.A_log._version or c[1].device != self.A_log.device or c[2] is not self.A_log:
+            with torch.no_grad():
+                c = (self.A_log._version, -torch.exp(self.A_log.float()), self.A_log)
+            self._A_cache = c
+        return c[1]
+
     def _D(self):
         return self.D.view(self.nheads, self.headdim) if self.D_has_hdim else self.D
 
@@ -106,7 +118,7 @@ class Mamba2(nn.Module):
         zxbcdt = self.in_proj(u)
         if seqlen_og is not None:
             zxbcdt = zxbcdt.view(batch, seqlen, zxbcdt.shape[-1])
-        A = -torch.exp(self.A_log.float())
+        A = self._A()
         dt_limit_kwargs = {} if self.dt_limit == (0.0, float("inf")) else dict(dt_limit=self.dt_limit)
         d_mlp = (zxbcdt.shape[-1] - 2 * self.d_ssm - 2 * self.ngroups * self.d_state - self.nheads) // 2
 
@@ -163,7 +175,7 @@ class Mamba2(nn.Module):
             zxbcdt, [d_mlp, d_mlp, self.d_ssm, self.d_ssm + 2 * self.ngroups * self.d_state, self.nheads], dim=-1)
         xBC = causal_conv1d_update(xBC, conv_state, self._conv_w(), self.conv1d.bias, self.activation)
         x, B, C = torch.split(xBC, [self.d_ssm, self.ngroups * self.d_state, self.ngroups * self.d_state], dim=-1)
-        A = -torch.exp(self.A_log.float())
+        A = self._A()
         batch = x.shape[0]
         H, P, N, G = self.nheads, self.headdim, self.d_state, self.ngroups
         # stride-0 broadcasts, exactly what upstream passes (einops.repeat): the kernel sees tied A/dt/D

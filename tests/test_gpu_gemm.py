@@ -90,3 +90,31 @@ def test_linear_autograd_matches_torch():
         assert e <= 5e-3, (name, e)
     y2 = linear(d[0].detach(), d[1].detach())
     assert excess_over_rounding(y2, F.linear(x.float(), w.float())) <= 1e-4
+
+
+@pytest.mark.parametrize("M,V,d,block", [(700, 16384, 2048, 256), (333, 1000, 256, 128), (64, 50288, 512, 64)])
+def test_linear_cross_entropy_matches_torch(M, V, d, block):
+    """Head GEMM + shifted-label cross-entropy in row blocks (interface.linear_ce): loss, dh and dW against
+    nn.CrossEntropyLoss on fp32 logits of the same bf16-valued operands; ignored labels included; the logits GEMMs, the
+    softmax statistics and the gradient (softmax - onehot) all run in libomnissm."""
+    from omnimamba_b200 import _cabi
+    from omnimamba_b200.interface.linear_ce import linear_cross_entropy
+    g = torch.Generator().manual_seed(M + V)
+    h, w = _rand((M, d), 21), _rand((V, d), 22, 0.05)
+    labels = torch.randint(0, V, (M,), generator=g)
+    labels[::5] = -100
+    hr, wr = h.float().requires_grad_(), w.float().requires_grad_()
+    ref = F.cross_entropy(hr @ wr.t(), labels, ignore_index=-100)
+    ref.backward()
+    hd, wd = h.to(DEV).requires_grad_(), w.to(DEV).requires_grad_()
+    _cabi.reset_launch_count()
+    loss = linear_cross_entropy(hd, wd, labels.to(DEV), block=block)
+    loss.backward()
+    torch.cuda.synchronize()
+    nb = (M + block - 1) // block
+    assert _cabi.launch_count() >= 6 * nb - 2, "per row block: 2 logits GEMMs, 2 CE kernels, dgrad and wgrad GEMMs"
+    e = abs(loss.item() - ref.item()) / abs(ref.item())
+    edh, edw = excess_over_rounding(hd.grad, hr.grad), rel_l2(wd.grad, wr.grad)
+    print(f"linear_cross_entropy M={M} V={V} d={d}: loss rel err {e:.2e}, dh excess {edh:.2e} (plain {rel_l2(hd.grad, hr.grad):.2e}), dW {edw:.2e}")
+    assert e <= 1e-5
+    assert edh <= 5e-3 and edw <= 5e-3     # the bf16 rounding of (softmax - onehot) before the two gradient GEMMs
