@@ -213,6 +213,21 @@ typedef struct omni_ssu_params {
 } omni_ssu_params_t;
 OMNI_API int omni_selective_state_update(const omni_ssu_params_t* p, void* stream);
 
+/* ---- single-token layer core (decode) ------------------------------------------------------- */
+/* The three kernels Mamba2.step launches between in_proj and out_proj, as one [mamba_ssm/modules/mamba2.py: step;
+ * captured per layer by /root/reference/models/stage2/generation.py:383-431]: causal_conv1d_update (+SiLU) on the xBC
+ * columns of zxbcdt, selective_state_update (dt_softplus, dt_bias, A tied over d_state, D per head) and the gated RMSNorm
+ * rmsnorm(y * silu(z)) * norm_weight (norm_before_gate = False, one group).  zxbcdt (B, 2 dim + 2 N + H), dim = 64 H;
+ * conv_state (B, dim + 2 N, W <= 4) and ssm_state (B, H, 64, 128) are updated IN PLACE; A (H) fp32 = -exp(A_log);
+ * out (B, dim).  Built for the OmniMamba geometry (nheads 64, headdim 64, d_state 128, ngroups 1); other geometries use the
+ * three separate entry points.  Graph-capturable (one cluster launch, no host synchronisation). */
+typedef struct omni_mamba2_decode_core_params {
+  omni_tensor_t zxbcdt, conv_state, conv_weight, conv_bias, ssm_state, A, D, dt_bias, norm_weight;
+  omni_tensor_t out;
+  float eps;
+} omni_mamba2_decode_core_params_t;
+OMNI_API int omni_mamba2_decode_core(const omni_mamba2_decode_core_params_t* p, void* stream);
+
 /* ---- Mamba-1 selective scan ---------------------------------------------------------------- */
 /* selective_scan_fn(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
  * [mamba_ssm/ops/selective_scan_interface.py; reachable via ssm_cfg.layer="Mamba1",
@@ -250,6 +265,27 @@ typedef struct omni_gemm_params {
 } omni_gemm_params_t;
 OMNI_API int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream);
 OMNI_API int omni_gemm_bf16_supported(void); /* 1 if the driver exports cuTensorMapEncodeTiled */
+
+/* ---- fused training forward (path A) --------------------------------------------------------- */
+/* mamba_split_conv1d_scan_combined forward [mamba_ssm/ops/triton/ssd_combined.py: MambaSplitConv1dScanCombinedFn.forward;
+ * called by Mamba2.forward when use_mem_eff_path and no cache, i.e. by every training step of
+ * /root/reference/models/stage2/block.py:117].  One call = causal conv1d + SiLU on the xBC columns of zxbcdt ->
+ * chunked SSD scan (dt = last nheads columns, dt_softplus) -> gated RMSNorm with z = first dim columns ->
+ * out_proj (bf16: omni_gemm_bf16).  Caller-owned intermediates (the backward reads them): xbc_conv (B, L, dim + 2 G N),
+ * scan_out (B, L, dim) pre-norm, rstd (B L) fp32, y (B, L, dim) normed.  rmsnorm_weight absent: the gate is applied inside
+ * the scan and y / rstd are unused.  outproj_weight (d_out, dim) bf16 absent: no projection, `out` unused.
+ * workspace: as omni_ssd_chunk_scan_fwd.  The backward is the composition omni_norm_gated_bwd -> omni_ssd_chunk_scan_bwd ->
+ * omni_causal_conv1d_bwd (+ omni_gemm_bf16 for out_proj), see INTEGRATION.md. */
+typedef struct omni_split_conv1d_scan_fwd_params {
+  omni_tensor_t zxbcdt, conv1d_weight, conv1d_bias, dt_bias, A, D, initial_states, seq_idx, rmsnorm_weight, outproj_weight;
+  omni_tensor_t xbc_conv, scan_out, rstd, y, out, final_states, workspace;
+  int32_t nheads, headdim, ngroups, dstate, chunk_size;
+  int32_t activation;       /* omni_activation_t */
+  int32_t norm_before_gate;
+  int32_t algo;             /* omni_ssd_algo_t */
+  float dt_min, dt_max, rmsnorm_eps;
+} omni_split_conv1d_scan_fwd_params_t;
+OMNI_API int omni_split_conv1d_scan_fwd(const omni_split_conv1d_scan_fwd_params_t* p, void* stream);
 
 /* ---- head loss ------------------------------------------------------------------------------ */
 /* Softmax cross-entropy over a block of fp32 logits (the img_head / lm_head GEMM output of omni_gemm_bf16) - the loss

@@ -101,6 +101,19 @@ class Gemm(C.Structure):
     _fields_ = _T("a", "b", "a2", "b2", "out")
 
 
+class SplitConv1dScanFwd(C.Structure):
+    _fields_ = _T("zxbcdt", "conv1d_weight", "conv1d_bias", "dt_bias", "A", "D", "initial_states", "seq_idx", "rmsnorm_weight",
+                  "outproj_weight", "xbc_conv", "scan_out", "rstd", "y", "out", "final_states", "workspace") + [
+        ("nheads", C.c_int32), ("headdim", C.c_int32), ("ngroups", C.c_int32), ("dstate", C.c_int32), ("chunk_size", C.c_int32),
+        ("activation", C.c_int32), ("norm_before_gate", C.c_int32), ("algo", C.c_int32),
+        ("dt_min", C.c_float), ("dt_max", C.c_float), ("rmsnorm_eps", C.c_float)]
+
+
+class DecodeCore(C.Structure):
+    _fields_ = _T("zxbcdt", "conv_state", "conv_weight", "conv_bias", "ssm_state", "A", "D", "dt_bias", "norm_weight", "out") + [
+        ("eps", C.c_float)]
+
+
 class SoftmaxCe(C.Structure):
     _fields_ = _T("logits", "labels", "lse", "loss", "scale", "grad") + [("ignore_index", C.c_int64)]
 
@@ -120,6 +133,8 @@ ENTRY_POINTS = {
     "omni_selective_scan_fwd": SelScanFwd,
     "omni_selective_scan_bwd": SelScanBwd,
     "omni_gemm_bf16": Gemm,
+    "omni_split_conv1d_scan_fwd": SplitConv1dScanFwd,
+    "omni_mamba2_decode_core": DecodeCore,
     "omni_softmax_ce_fwd": SoftmaxCe,
     "omni_softmax_ce_bwd": SoftmaxCe,
 }

@@ -212,34 +212,47 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
         xBC = zxbcdt[..., dim:dim + conv_dim]
         dt = zxbcdt[..., dim + conv_dim:]
         act = abi.ACT_NONE if activation is None else abi.ACT_SILU
-        xBC_conv = torch.empty(batch, seqlen, conv_dim, device=zxbcdt.device, dtype=zxbcdt.dtype)
-        conv1d_fwd_raw(xBC.transpose(1, 2), conv1d_weight, conv1d_bias, seq_idx, None, xBC_conv.transpose(1, 2), None, act)
-        x = xBC_conv[..., :dim].view(batch, seqlen, nheads, headdim)
-        Bm = xBC_conv[..., dim:dim + ngroups * dstate].view(batch, seqlen, ngroups, dstate)
-        Cm = xBC_conv[..., dim + ngroups * dstate:].view(batch, seqlen, ngroups, dstate)
-        zh = z.view(batch, seqlen, nheads, headdim)
-        scan_out, fin = ssd_fwd_raw(x, dt, A, Bm, Cm, chunk_size, D, zh if rmsnorm_weight is None else None, dt_bias,
-                                    initial_states, seq_idx, True, dt_limit, return_final_states)
-        rstd = None
+        dev, dt_ = zxbcdt.device, zxbcdt.dtype
+        xBC_conv = torch.empty(batch, seqlen, conv_dim, device=dev, dtype=dt_)
+        scan_out = torch.empty(batch, seqlen, dim, device=dev, dtype=dt_)
+        fin = torch.empty(batch, nheads, headdim, dstate, device=dev, dtype=torch.float32) if return_final_states else None
+        rstd = y = None
         if rmsnorm_weight is not None:
             rmsnorm_weight = rmsnorm_weight.contiguous()
-            y, _, rstd = norm_gated_fwd_raw(scan_out.view(batch * seqlen, dim), rmsnorm_weight, None,
-                                            z.reshape(batch * seqlen, dim), rmsnorm_eps, dim // ngroups,
-                                            norm_before_gate, True)
-            y = y.view(batch, seqlen, dim)
-        else:
+            rstd = torch.empty(batch * seqlen * ngroups, device=dev, dtype=torch.float32)
+            y = torch.empty(batch, seqlen, dim, device=dev, dtype=dt_)
+        # out_proj inside the same call when its operands are bf16 (autocast / bf16 model): the tcgen05 GEMM
+        ac = _autocast_dtype()
+        w, b_ = outproj_weight, outproj_bias
+        if w is not None and ac is not None:
+            w = w.to(ac)
+            b_ = b_.to(ac) if b_ is not None else None
+        fuse_gemm = (w is not None and w.dtype == torch.bfloat16 and dt_ == torch.bfloat16 and w.stride(-1) == 1
+                     and w.stride(0) % 8 == 0 and w.data_ptr() % 16 == 0 and w.shape[0] % 8 == 0 and abi.gemm_supported())
+        out = torch.empty(batch, seqlen, w.shape[0], device=dev, dtype=torch.bfloat16) if fuse_gemm else None
+        nws = abi.ssd_fwd_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate) if dt_ == torch.bfloat16 else 0
+        ws = torch.empty(nws, device=dev, dtype=torch.uint8) if nws > 0 else None
+        p = abi.SplitConv1dScanFwd()
+        p.zxbcdt, p.conv1d_weight, p.conv1d_bias = abi.tdesc(zxbcdt), abi.tdesc(conv1d_weight), abi.tdesc(conv1d_bias)
+        p.dt_bias, p.A, p.D = abi.tdesc(dt_bias.contiguous()), abi.tdesc(A), abi.tdesc(D)
+        p.initial_states, p.seq_idx = abi.tdesc(_last_contig(initial_states)), abi.tdesc(seq_idx)
+        p.rmsnorm_weight, p.outproj_weight = abi.tdesc(rmsnorm_weight), abi.tdesc(w if fuse_gemm else None)
+        p.xbc_conv, p.scan_out, p.rstd, p.y, p.out = (abi.tdesc(t) for t in (xBC_conv, scan_out, rstd, y, out))
+        p.final_states, p.workspace = abi.tdesc(fin), abi.tdesc(ws)
+        p.nheads, p.headdim, p.ngroups, p.dstate, p.chunk_size = nheads, headdim, ngroups, dstate, int(chunk_size)
+        p.activation, p.norm_before_gate, p.algo = act, int(bool(norm_before_gate)), abi.SSD_AUTO
+        p.dt_min, p.dt_max, p.rmsnorm_eps = float(dt_limit[0]), float(min(dt_limit[1], 3.0e38)), float(rmsnorm_eps)
+        abi.call("omni_split_conv1d_scan_fwd", p, dev)     # conv1d + SiLU -> scan -> gated norm (-> out_proj): one C-ABI call
+        scan_out = scan_out.view(batch, seqlen, nheads, headdim)
+        if y is None:
             y = scan_out.view(batch, seqlen, dim)
         ctx.outproj_weight_dtype = outproj_weight.dtype if outproj_weight is not None else None
-        if outproj_weight is not None:
-            ac = _autocast_dtype()
-            w, b_ = outproj_weight, outproj_bias
-            if ac is not None:
-                w = w.to(ac)
-                b_ = b_.to(ac) if b_ is not None else None
-                y = y.to(ac)
-            else:
-                y = y.to(w.dtype)
-            out = mm_nt(y.reshape(batch * seqlen, dim), w).view(batch, seqlen, w.shape[0])
+        if fuse_gemm:
+            if b_ is not None:
+                out = out + b_
+        elif w is not None:
+            y2 = (y.to(ac) if ac is not None else y.to(w.dtype)).reshape(batch * seqlen, dim)
+            out = mm_nt(y2, w).view(batch, seqlen, w.shape[0])
             if b_ is not None:
                 out = out + b_
         else:

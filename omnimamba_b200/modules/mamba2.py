@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..interface.causal_conv1d import causal_conv1d_fn, causal_conv1d_update
+from ..interface.decode import decode_core_supported, mamba2_decode_core
 from ..interface.gemm import Linear
 from ..interface.layernorm_gated import RMSNorm as RMSNormGated
 from ..interface.selective_state_update import selective_state_update
@@ -171,6 +172,13 @@ class Mamba2(nn.Module):
         assert hidden_states.shape[1] == 1, "Only support decoding with 1 token at a time for now"
         zxbcdt = self.in_proj(hidden_states.squeeze(1))
         d_mlp = (zxbcdt.shape[-1] - 2 * self.d_ssm - 2 * self.ngroups * self.d_state - self.nheads) // 2
+        if (d_mlp == 0 and self.rmsnorm and not self.norm_before_gate and not self.D_has_hdim and self.d_ssm == self.d_inner
+                and decode_core_supported(self.nheads, self.headdim, self.d_state, self.ngroups, self.d_conv)
+                and zxbcdt.stride(-1) == 1 and ssm_state.is_contiguous()):
+            # conv update + state update + gated norm in ONE kernel (the OmniMamba geometry; csrc/decode_core.cu)
+            y = mamba2_decode_core(zxbcdt, conv_state, self._conv_w(), self.conv1d.bias, ssm_state, self._A(), self.D,
+                                   self.dt_bias, self.norm.weight, self.norm.eps)
+            return self.out_proj(y).unsqueeze(1), conv_state, ssm_state
         z0, x0, z, xBC, dt = torch.split(
             zxbcdt, [d_mlp, d_mlp, self.d_ssm, self.d_ssm + 2 * self.ngroups * self.d_state, self.nheads], dim=-1)
         xBC = causal_conv1d_update(xBC, conv_state, self._conv_w(), self.conv1d.bias, self.activation)

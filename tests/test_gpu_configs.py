@@ -254,3 +254,79 @@ def test_scan_vs_flashinfer_ssd_combined():
     print("scan (2,1024,64,64) bf16: " + ", ".join(f"{k} {v:.2e}" for k, v in res.items()))
     assert res["ours vs flashinfer"] <= 6e-3
     assert res["ours vs oracle"] <= res["flashinfer vs oracle"] * 1.05 + 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (5) decode: the fused single-token layer core (conv update + state update + gated norm, one cluster kernel)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_decode_core_matches_oracle_and_unfused_step(dtype):
+    """Mamba2(2048).step at batch 3: four single-token steps after a prefill, (a) fp32 against the oracle's mamba2_step_ref
+    (outputs and both caches), (b) the fused kernel against the three separate kernels of the same module in the same
+    dtype, (c) replayed from a CUDA graph."""
+    from omnimamba_b200 import _cabi
+    import omnimamba_b200.modules.mamba2 as m2
+    d_model, B, L0, steps = 2048, 3, 9, 4
+    p = oracle.mamba2_init_params(d_model, seed=11)
+    g = torch.Generator().manual_seed(12)
+    u = torch.randn(B, L0 + steps, d_model, generator=g)
+    sd = {k: v.detach() for k, v in _state_dict(p).items()}
+
+    def run(fused, dt):
+        m = m2.Mamba2(d_model, layer_idx=0, device=DEV, dtype=dt)
+        m.load_state_dict({k: v.to(DEV, dt) for k, v in sd.items()})
+        ip = type("IP", (), {"seqlen_offset": 0, "key_value_memory_dict": {}})()
+        old = m2.decode_core_supported
+        m2.decode_core_supported = old if fused else (lambda *a: False)
+        outs = []
+        try:
+            with torch.no_grad():
+                m(u[:, :L0].to(DEV, dt), inference_params=ip)
+                ip.seqlen_offset = L0
+                _cabi.reset_launch_count()
+                for t in range(steps):
+                    outs.append(m(u[:, L0 + t:L0 + t + 1].to(DEV, dt), inference_params=ip))
+                launches = _cabi.launch_count()
+        finally:
+            m2.decode_core_supported = old
+        conv, ssm = ip.key_value_memory_dict[0]
+        return torch.cat(outs, 1), conv.clone(), ssm.clone(), launches, m, ip
+
+    yf, cf, sf, nf, m, ip = run(True, dtype)
+    yu, cu, su, nu, _, _ = run(False, dtype)
+    torch.cuda.synchronize()
+    assert nf < nu, (nf, nu)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    e = {"y": rel_l2(yf, yu), "conv_state": rel_l2(cf, cu), "ssm_state": rel_l2(sf, su)}
+    print(f"decode core {dtype}: fused vs unfused " + ", ".join(f"{k} {v:.2e}" for k, v in e.items()) + f"; launches/step {nf / steps:.1f} vs {nu / steps:.1f}")
+    assert e["y"] <= tol and e["conv_state"] <= 1e-6 and e["ssm_state"] <= (1e-5 if dtype == torch.float32 else 5e-3)
+    if dtype == torch.float32:
+        conv_r = torch.zeros(B, p.conv_dim, p.d_conv)
+        ssm_r = torch.zeros(B, p.nheads, p.headdim, p.d_state)
+        with torch.no_grad():
+            oracle.mamba2_forward_ref(p, u[:, :L0], conv_state=conv_r, ssm_state=ssm_r)
+            yr = torch.cat([oracle.mamba2_step_ref(p, u[:, L0 + t:L0 + t + 1], conv_r, ssm_r) for t in range(steps)], 1)
+        eo = {"y": rel_l2(yf, yr), "conv_state": rel_l2(cf, conv_r), "ssm_state": rel_l2(sf, ssm_r)}
+        print("decode core fp32 vs oracle step: " + ", ".join(f"{k} {v:.2e}" for k, v in eo.items()))
+        assert max(eo.values()) <= 5e-5
+    # (c) graph replay of one more fused step equals the eager step on cloned caches
+    conv, ssm = ip.key_value_memory_dict[0]
+    c0, s0 = conv.clone(), ssm.clone()
+    tok = u[:, -1:].to(DEV, dtype)
+    with torch.no_grad():
+        y_eager = m(tok, inference_params=ip)
+        c1, s1 = conv.clone(), ssm.clone()
+        conv.copy_(c0); ssm.copy_(s0)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m(tok, inference_params=ip)
+        torch.cuda.current_stream().wait_stream(side)
+        conv.copy_(c0); ssm.copy_(s0)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            y_graph = m(tok, inference_params=ip)
+        conv.copy_(c0); ssm.copy_(s0)
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y_graph, y_eager) and torch.equal(conv, c1) and torch.equal(ssm, s1)
