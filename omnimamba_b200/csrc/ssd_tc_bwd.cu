@@ -424,6 +424,26 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       atomicAdd(&dst[row], part);
     };
     if (!fresh) dot_c_acc(tab->rbase[0]);  // what the dC accumulator already holds from earlier items of the group
+    // (both of these only need what is already there: they run while G2 executes)
+    {  // zc_h = <dS_{c+1}, S_c> over the head's 64 rows: the two fp16 tiles share their (swizzled) layout, so it is an
+       // elementwise product of equal offsets - 32 values per thread (it used to be the trace of a 128 x 128 x 128 GEMM)
+      const uint4* st = reinterpret_cast<const uint4*>(smem + SM_S);
+      const uint4* dst = reinterpret_cast<const uint4*>(smem + SM_DS);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int slot = warp * 128 + k * 32 + lane;      // 16-byte slot; row = (slot >> 3) & 127: a warp stays inside one head
+        const uint4 sv = st[slot], dv = dst[slot];
+        const uint32_t sw4[4] = {sv.x, sv.y, sv.z, sv.w}, dw4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a2 = h2f2(sw4[e]), b2 = h2f2(dw4[e]);
+          acc += a2.x * b2.x + a2.y * b2.y;
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) atomicAdd(&tab->zc[(warp >> 2) & 1], acc);   // slots [warp * 128, +128): rows 16 (warp & 7) .. +15 of n-half warp >> 3
+    }
     // ---- F. dx_j = dt_j (wd_j + es_j ws_j) + D dy_j; x.w and x.wd row sums; one head at a time through the staging tile --
     mbar_wait(&bars[BB_C2], ph);
     BTR(6);
@@ -550,30 +570,8 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
       }
     }
-    // ---- L. x16 -> X' = es dt x, dy16 -> exp(lam_i) dy, in place (packed fp16 multiplies) ----------------------------------
-    mbar_wait(&bars[BB_C5], ph);
-    BTR(12);
-    tc_fence_after();
-    dot_c_acc(tab->rr[1]);  // base + (M_0 + M_1) B: both heads' within-chunk parts
-    {  // zc_h = <dS_{c+1}, S_c> over the head's 64 rows: the two fp16 tiles share their (swizzled) layout, so it is an
-       // elementwise product of equal offsets - 32 values per thread (it used to be the trace of a 128 x 128 x 128 GEMM)
-      const uint4* st = reinterpret_cast<const uint4*>(smem + SM_S);
-      const uint4* dst = reinterpret_cast<const uint4*>(smem + SM_DS);
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int slot = warp * 128 + k * 32 + lane;      // 16-byte slot; row = (slot >> 3) & 127: a warp stays inside one head
-        const uint4 sv = st[slot], dv = dst[slot];
-        const uint32_t sw4[4] = {sv.x, sv.y, sv.z, sv.w}, dw4[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 a2 = h2f2(sw4[e]), b2 = h2f2(dw4[e]);
-          acc += a2.x * b2.x + a2.y * b2.y;
-        }
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) atomicAdd(&tab->zc[(warp >> 2) & 1], acc);   // slots [warp * 128, +128): rows 16 (warp & 7) .. +15 of n-half warp >> 3
-    }
+    // ---- L. x16 -> X' = es dt x, dy16 -> exp(lam_i) dy, in place (packed fp16 multiplies) - BEFORE waiting for G5 / G7 of head 1:
+    //         those read M_1 / MT_1 (TMEM) and the B / C tiles, not x / dy, so the scaling runs under them ---------------
     {
       uint4* xt = reinterpret_cast<uint4*>(smem + SM_X);
 #pragma unroll 2
@@ -588,6 +586,10 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         xt[slot] = v;
       }
     }
+    mbar_wait(&bars[BB_C5], ph);
+    BTR(12);
+    tc_fence_after();
+    dot_c_acc(tab->rr[1]);  // base + (M_0 + M_1) B: both heads' within-chunk parts
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
