@@ -1133,7 +1133,9 @@ struct CombineArgs {
   const float* local;     // [B * k][H][64][128] state each piece ends with from a zero start
   const float* decay;     // [B * k][H]
   float* enter;           // [B * k][H][64][128] state each piece starts from
+  float* fin;             // optional [B][H][64][128]: the state after the last piece of the chain
   int B, k, H;
+  int reverse;            // 1: the chain runs from the last piece to the first (reverse sweep of the backward)
 };
 __global__ void __launch_bounds__(256) ssd_piece_combine_kernel(CombineArgs a) {
   const int64_t per = (int64_t)a.H * HD * NS, total = (int64_t)a.B * per;
@@ -1142,11 +1144,13 @@ __global__ void __launch_bounds__(256) ssd_piece_combine_kernel(CombineArgs a) {
     const int64_t r = i - b * per;
     const int h = (int)(r / (HD * NS)), pn = (int)(r - (int64_t)h * HD * NS), pp = pn / NS, n = pn - pp * NS;
     float S = a.init ? ld_any(a.init, a.init_dtype, b * a.i_b + (int64_t)h * a.i_h + (int64_t)pp * a.i_p + n) : 0.f;
-    for (int p = 0; p < a.k; ++p) {
+    for (int step = 0; step < a.k; ++step) {
+      const int p = a.reverse ? a.k - 1 - step : step;
       const int64_t o = ((int64_t)(b * a.k + p)) * per + r;
       a.enter[o] = S;
-      if (p + 1 < a.k) S = a.decay[(int64_t)(b * a.k + p) * a.H + h] * S + a.local[o];
+      if (step + 1 < a.k || a.fin != nullptr) S = a.decay[(int64_t)(b * a.k + p) * a.H + h] * S + a.local[o];
     }
+    if (a.fin != nullptr) a.fin[i] = S;
   }
 }
 __global__ void __launch_bounds__(256) ssd_piece_final_kernel(const float* piece_fin, float* fin, int B, int k, int64_t per) {
@@ -1453,13 +1457,70 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
 int ssd_tc_state_sweep(int mode, const omni_tensor_t& xlike, const omni_tensor_t& dt, const omni_tensor_t& A,
                        const omni_tensor_t& dt_bias, const omni_tensor_t& init, const omni_tensor_t& fin, const void* ws_bslot,
                        void* ws_states, int64_t G, int dt_softplus, float dt_min, float dt_max, cudaStream_t s,
-                       void* hand_slots) {
+                       void* hand_slots, void* piece_ws) {
   omni_tensor_t none{};
   float* hand = static_cast<float*>(hand_slots);
   int* flags = hand_slots ? reinterpret_cast<int*>(static_cast<char*>(hand_slots) + (size_t)kHandSlots * 128 * NS * sizeof(float))
                           : nullptr;
+  // piece schedule (few long sequences), as in the forward: a store-free sweep gives the state every piece ends with from
+  // a zero start, the chain over the pieces (last to first in the reverse sweep) gives the state each one enters with,
+  // and the real sweep then runs on k times as many independent sequences
+  const int64_t Bsz = xlike.shape[0], L = xlike.shape[1], H = xlike.shape[2];
+  int k = piece_ws != nullptr ? piece_count(Bsz, L, H) : 1;
+  while (k > 1 && (L / k) % Q != 0) --k;     // (the per-chunk state tensor is addressed per piece: pieces are whole chunks)
+  if (k > 1 && L % k != 0) k = 1;
+  omni_tensor_t xv, dtv;
+  if (k > 1 && !(piece_view(xlike, k, xv) && piece_view(dt, k, dtv))) k = 1;
+  if (k > 1) {
+    const int64_t Bk = Bsz * k, per = H * HD * NS;
+    float* local = static_cast<float*>(piece_ws);
+    float* enter = local + Bk * per;
+    float* decay = enter + Bk * per;
+    auto state_tensor = [&](float* ptr) {
+      omni_tensor_t t{};
+      t.data = ptr; t.dtype = OMNI_F32; t.ndim = 4;
+      t.shape[0] = Bk; t.shape[1] = H; t.shape[2] = HD; t.shape[3] = NS;
+      t.stride[3] = 1; t.stride[2] = NS; t.stride[1] = HD * NS; t.stride[0] = per;
+      return t;
+    };
+    if (int rc = tc_launch(mode, xv, dtv, A, none, dt_bias, none, state_tensor(local), none, ws_bslot, nullptr, nullptr, G,
+                           dt_softplus, dt_min, dt_max, s, hand, flags, true))
+      return rc;
+    PieceArgs pa{};
+    pa.dt = dtv.data; pa.A = static_cast<const float*>(A.data); pa.dt_bias = dt_bias.data;
+    pa.dt_b = dtv.stride[0]; pa.dt_l = dtv.stride[1]; pa.dt_h = dtv.stride[2];
+    pa.Bk = (int)Bk; pa.Lp = (int)(L / k); pa.H = (int)H;
+    pa.dt_dtype = dtv.dtype; pa.dtb_dtype = dt_bias.dtype; pa.dt_softplus = dt_softplus;
+    pa.dt_min = dt_min; pa.dt_max = dt_max; pa.decay = decay;
+    ssd_piece_decay_kernel<<<dim3((unsigned)H, (unsigned)Bk), 256, 0, s>>>(pa);
+    OMNI_CUDA_LAUNCH_CHECK("ssd_piece_decay_kernel");
+    CombineArgs ca{};
+    if (present(init)) {
+      OMNI_CHECK(shape_is(init, 4, Bsz, H, HD, NS) && is_float_dtype(init.dtype) && init.stride[3] == 1, OMNI_BAD_SHAPE,
+                 "ssd: initial / final state gradients must be (B, H, P, N)");
+      ca.init = init.data; ca.init_dtype = init.dtype; ca.i_b = init.stride[0]; ca.i_h = init.stride[1]; ca.i_p = init.stride[2];
+    }
+    if (present(fin)) {
+      OMNI_CHECK(shape_is(fin, 4, Bsz, H, HD, NS) && fin.dtype == OMNI_F32 && fin.stride[3] == 1 && fin.stride[2] == NS &&
+                     fin.stride[1] == HD * NS && fin.stride[0] == per,
+                 OMNI_BAD_SHAPE, "ssd: the sweep's last state must be contiguous fp32 (B, H, P, N)");
+      ca.fin = static_cast<float*>(fin.data);
+    }
+    ca.local = local; ca.decay = decay; ca.enter = enter; ca.B = (int)Bsz; ca.k = k; ca.H = (int)H; ca.reverse = mode == 2;
+    ssd_piece_combine_kernel<<<sm_count() * 4, 256, 0, s>>>(ca);
+    OMNI_CUDA_LAUNCH_CHECK("ssd_piece_combine_kernel");
+    return tc_launch(mode, xv, dtv, A, none, dt_bias, state_tensor(enter), none, none, ws_bslot, nullptr, ws_states, G, dt_softplus,
+                     dt_min, dt_max, s, hand, flags);
+  }
   return tc_launch(mode, xlike, dt, A, none, dt_bias, init, fin, none, ws_bslot, nullptr, ws_states, G, dt_softplus, dt_min,
                    dt_max, s, hand, flags);
+}
+
+// scratch of the sweeps' piece schedule (both sweeps share it): two per-piece state tensors + the piece decays
+int64_t ssd_tc_sweep_piece_bytes(int64_t Bsz, int64_t L, int64_t H) {
+  const int k = piece_count(Bsz, L, H);
+  if (k <= 1) return 0;
+  return 2 * Bsz * k * H * HD * NS * (int64_t)sizeof(float) + Bsz * k * H * (int64_t)sizeof(float) + 1024;
 }
 
 int64_t ssd_tc_hand_bytes() { return (int64_t)kHandSlots * (128 * NS * (int64_t)sizeof(float) + sizeof(int)) + 256; }

@@ -738,7 +738,8 @@ int g_btrace_items = 0;
 int ssd_tc_state_sweep(int mode, const omni_tensor_t& xlike, const omni_tensor_t& dt, const omni_tensor_t& A,
                        const omni_tensor_t& dt_bias, const omni_tensor_t& init, const omni_tensor_t& fin, const void* ws_bslot,
                        void* ws_states, int64_t G, int dt_softplus, float dt_min, float dt_max, cudaStream_t s,
-                       void* hand_slots);
+                       void* hand_slots, void* piece_ws);
+int64_t ssd_tc_sweep_piece_bytes(int64_t Bsz, int64_t L, int64_t H);
 int64_t ssd_tc_hand_bytes();  // state hand-off slots + flags of the half-item schedule (one set per sweep)
 int ssd_tc_prep(const omni_tensor_t& Bm, const omni_tensor_t& Cm, void* wsB, void* wsC, cudaStream_t s);
 
@@ -746,7 +747,7 @@ int64_t ssd_tc_bwd_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads
   const int64_t nchunks = (seqlen + Q - 1) / Q;
   const int64_t bc = 2 * batch * seqlen * ngroups * NS * 2;            // fp16 copies of B and C
   const int64_t st = batch * nchunks * nheads * HD * NS * 2;           // fp16 states, one tensor
-  return ((bc + 255) / 256) * 256 + 2 * st + 256 + 2 * ssd_tc_hand_bytes();
+  return ((bc + 255) / 256) * 256 + 2 * st + 256 + 2 * ssd_tc_hand_bytes() + 256 + ssd_tc_sweep_piece_bytes(batch, seqlen, nheads);
 }
 
 bool ssd_tc_bwd_supported(const omni_ssd_bwd_params_t* p) {
@@ -810,16 +811,19 @@ int ssd_tc_bwd(const omni_ssd_bwd_params_t* p, cudaStream_t s) {
   __half* wsDS = reinterpret_cast<__half*>(ws + bc + st_bytes);
   uint8_t* hand = ws + bc + 2 * st_bytes;
   hand += (256 - reinterpret_cast<uintptr_t>(hand) % 256) % 256;
+  uint8_t* piece_ws = hand + 2 * ssd_tc_hand_bytes();
+  piece_ws += (256 - reinterpret_cast<uintptr_t>(piece_ws) % 256) % 256;
+  if (ssd_tc_sweep_piece_bytes(Bsz, L, H) == 0) piece_ws = nullptr;
 
   if (int rc = ssd_tc_prep(Bm, Cm, wsB, wsC, s)) return rc;
   omni_tensor_t none{};
   // forward states S_c (x, B, sj) and reverse state gradients dS_{c+1} (dy, C, exp(lam)); the reverse sweep's final
   // state is dS_0 = the gradient of initial_states
   if (int rc = ssd_tc_state_sweep(1, x, dt, p->A, p->dt_bias, p->initial_states, none, wsB, wsS, G, p->dt_softplus, p->dt_min,
-                                  p->dt_max, s, hand))
+                                  p->dt_max, s, hand, piece_ws))
     return rc;
   if (int rc = ssd_tc_state_sweep(2, dy, dt, p->A, p->dt_bias, p->dfinal_states, p->dinitial_states, wsC, wsDS, G, p->dt_softplus,
-                                  p->dt_min, p->dt_max, s, hand + ssd_tc_hand_bytes()))
+                                  p->dt_min, p->dt_max, s, hand + ssd_tc_hand_bytes(), piece_ws))
     return rc;
 
   BwdArgs a{};

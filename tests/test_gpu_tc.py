@@ -359,3 +359,30 @@ def test_ssd_tc_bwd_half_item_schedule(B, L, H):
         print(f"bwd half-item schedule B={B} L={L} H={H}: {nme} {e:.2e}")
         # (the per-head sums dA / ddt_bias cancel heavily: 3e-2 as in test_ssd_tc_bwd, upstream's own bf16 tolerance)
         assert e < (3e-2 if nme in ("dA", "ddt_bias") else 1e-2), (nme, e)
+
+
+@pytest.mark.parametrize("B,L,H", [(1, 8192, 8), (2, 4096, 4), (1, 16384, 64)])
+def test_ssd_tc_bwd_piece_schedule(B, L, H):
+    """Few long sequences: both state sweeps of the backward run on k independent pieces per sequence (store-free sweep ->
+    piece decays -> chain, last piece first in the reverse sweep -> real sweep from the entering states).  Tensor-core backward
+    against the exact fp32 SIMT backward on the device, with initial states and a gradient flowing into the final states."""
+    from omnimamba_b200.interface.ssd_combined import ssd_bwd_raw
+    g = torch.Generator(device=DEV).manual_seed(B * L + H)
+    P, N = 64, 128
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g).bfloat16()
+    x, dt, Bm, Cm, dy = rn(B, L, H, P), rn(B, L, H), rn(B, L, 1, N), rn(B, L, 1, N), rn(B, L, H, P)
+    A = -(torch.rand(H, device=DEV, generator=g) * 15 + 1)
+    A[0] = -0.01   # a head that barely decays: the chain over the pieces carries real weight
+    dt_bias = torch.rand(H, device=DEV, generator=g) * 4 - 6
+    D = torch.ones(H, device=DEV)
+    init = torch.randn(B, H, P, N, device=DEV, generator=g)
+    dfin = torch.randn(B, H, P, N, device=DEV, generator=g) * 0.1
+    kw = dict(D=D, dt_bias=dt_bias, dt_softplus=True, initial_states=init, dfinal_states=dfin, want_dinitial=True)
+    ref = ssd_bwd_raw(dy, x, dt, A, Bm, Cm, 256, algo="recurrent", **kw)
+    got = ssd_bwd_raw(dy, x, dt, A, Bm, Cm, 256, algo="chunked_tc", **kw)
+    torch.cuda.synchronize()
+    names = ["dx", "ddt", "dA", "dB", "dC", "dD", "dz", "ddt_bias", "dinit"]
+    errs = {n: rel_l2(t, r) for n, r, t in zip(names, ref, got) if r is not None}
+    print(f"bwd piece schedule B={B} L={L} H={H}: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v < (3e-2 if k in ("dA", "ddt_bias") else 1e-2), (k, v)
