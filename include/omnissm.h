@@ -265,6 +265,8 @@ typedef struct omni_gemm_params {
 } omni_gemm_params_t;
 OMNI_API int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream);
 OMNI_API int omni_gemm_bf16_supported(void); /* 1 if the driver exports cuTensorMapEncodeTiled */
+/* debug: tile scheme of omni_gemm_bf16 - 0 automatic, 1 single-CTA 128 x 256 tiles only, 2 CTA pairs (256 x 256) whenever legal */
+OMNI_API void omni_debug_set_gemm_mode(int mode);
 
 /* ---- fused training forward (path A) --------------------------------------------------------- */
 /* mamba_split_conv1d_scan_combined forward [mamba_ssm/ops/triton/ssd_combined.py: MambaSplitConv1dScanCombinedFn.forward;

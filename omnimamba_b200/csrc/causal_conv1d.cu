@@ -509,9 +509,11 @@ bool try_launch_bwd_fast(const ConvArgs& a, int W, const omni_tensor_t& x, const
              (t.shape[2] <= 1 || t.stride[2] % 4 == 0);
     };
     if (!ok8(x) || !ok8(g) || !ok8(dx)) return false;
-    // tokens per thread: 256 when there is enough work to fill the GPU with it (4x fewer partial-sum atomics), else 64
+    // tokens per thread: 256 when the sequences are long enough to keep every segment of a block busy with it and there is
+    // enough work to fill the GPU (4x fewer partial-sum atomics), else 64 (L = 329, the stage-1 training length, with 256:
+    // one segment of 256 tokens, one of 73 and idle ones - the kernel ran at 20 % of the HBM roofline there)
     const int64_t cols = (a.D + 127) / 128;
-    const int tl = cols * a.B * ((a.L + kSegs * 256 - 1) / (kSegs * 256)) >= 4 * (int64_t)sm_count() ? 256 : 64;
+    const int tl = (a.L >= kSegs * 256 && cols * a.B * ((a.L + kSegs * 256 - 1) / (kSegs * 256)) >= 4 * (int64_t)sm_count()) ? 256 : 64;
     dim3 block(32, kSegs), grid((unsigned)cols, (a.L + kSegs * tl - 1) / (kSegs * tl), a.B);
     if (a.silu) conv1d_bwd_fast_kernel<T, true><<<grid, block, 0, s>>>(a, tl);
     else conv1d_bwd_fast_kernel<T, false><<<grid, block, 0, s>>>(a, tl);

@@ -36,6 +36,7 @@ constexpr uint32_t SLAB_BYTES = 128 * 128;  // 128 rows x 128 B (64 bf16 or 32 f
 constexpr uint32_t G_EPI = 4 * (A_BYTES + 256 * BK * 2);   // = 8 * (A_BYTES + 64 * BK * 2): both shapes use 192 KB of stages
 constexpr uint32_t G_BAR = G_EPI + 2 * SLAB_BYTES;
 constexpr int kMaxStages = 8;
+int g_gemm_mode = 0;   // debug (omni_debug_set_gemm_mode): 0 auto, 1 single-CTA tiles only, 2 CTA pairs whenever the shape allows
 enum { GB_FULL = 0, GB_EMPTY = kMaxStages, GB_ACC_FULL = 2 * kMaxStages, GB_ACC_EMPTY = 2 * kMaxStages + 2, GB_COUNT = 2 * kMaxStages + 4 };
 constexpr uint32_t G_TMEMPTR = G_BAR + GB_COUNT * 8;
 constexpr uint32_t G_SMEM = G_TMEMPTR + 16;
@@ -230,6 +231,239 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   if (warp == 1) tmem_dealloc(tb, kTmemCols);
 }
 
+// ---- 2-CTA variant (cta_group::2): a pair of CTAs on the two SMs of a TPC works on ONE 256 x 256 tile ------------------
+// CTA r of the pair stages rows [128 r, +128) of A and rows [128 r, +128) of B; the leader's single MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256): each SM multiplies its own half of A with BOTH halves of B (the peer's half comes out
+// of the peer's shared memory) into its own TMEM.  Per 256 x 256 x 64 step a CTA loads 32 KB instead of 48 KB for a
+// 128 x 256 tile: a third less L2 -> SM traffic per flop (the 1-CTA kernel moves ~16 TB/s out of L2 at 1.4 PFLOP/s, which is
+// where it saturates) and half the shared-memory reads of B per SM.  Six 32 KB stages.
+//   full[s]   (leader's) : both CTAs' TMA loads of stage s (complete_tx on the leader's barrier) + the leader's expect_tx
+//   empty[s]  (each CTA) : tcgen05.commit multicast to both CTAs - the MMAs have read stage s
+//   acc_full  (each CTA) : commit multicast - the tile's accumulators are complete;   acc_empty (leader's): 4 + 4 epilogue warps
+constexpr int kStages2 = 6;
+constexpr uint32_t STAGE2_BYTES = 2 * A_BYTES;   // A 128 x 64 + B 128 x 64 per CTA
+static_assert(kStages2 * STAGE2_BYTES <= G_EPI, "stage ring (2-CTA)");
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {  // shared::cta address -> shared::cluster address in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a tile into THIS CTA's shared memory whose bytes are counted on the barrier at cluster address `bar_cluster`
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ss_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_2sm(uint64_t* bar) {  // arrives on `bar` (same offset) in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
+                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
+                const __grid_constant__ CUtensorMap mapC, GemmArgs a) {
+  constexpr int BN = 256;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_BAR);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G_TMEMPTR);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages2; ++i) {
+      mbar_init(&bars[GB_FULL + i], 1);
+      mbar_init(&bars[GB_EMPTY + i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[GB_ACC_FULL + i], 1);
+      mbar_init(&bars[GB_ACC_EMPTY + i], 8);   // four epilogue warps of each CTA
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // (the same warp of both CTAs)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB1); tma_prefetch_desc(&mapC);
+    if (a.K2 > 0) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // both CTAs' barriers are initialised before either touches the other's
+  tc_fence_after();
+  const uint32_t tb = *tmem_ptr;
+
+  const int tiles_m2 = (a.M + 255) / 256;
+  const int ntiles = tiles_m2 * a.tiles_n;
+  const int nk1 = (a.K1 + BK - 1) / BK, nk2 = (a.K2 + BK - 1) / BK, nk = nk1 + nk2;
+  auto coords = [&](int t, int& m0, int& n0) {   // groups of kGroupM / 2 row blocks of 256 x all column blocks (L2 reuse)
+    constexpr int GM = kGroupM / 2;
+    const int per_group = GM * a.tiles_n;
+    const int g = t / per_group, r = t - g * per_group;
+    const int first_m = g * GM;
+    const int gm = min(GM, tiles_m2 - first_m);
+    m0 = (first_m + r % gm) * 256;
+    n0 = (r / gm) * BN;
+  };
+
+  if (warp == 0) {
+    // ============ TMA producer (both CTAs): own halves of A and B, bytes counted on the LEADER's full barrier ==============
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        int m0, n0;
+        coords(t, m0, n0);
+        m0 += 128 * (int)rank;
+        n0 += 128 * (int)rank;
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+          const uint32_t s = it % kStages2, ph = (it / kStages2) & 1;
+          mbar_wait(&bars[GB_EMPTY + s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE2_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          if (rank == 0) mbar_expect_tx(&bars[GB_FULL + s], 2 * STAGE2_BYTES);
+          const uint32_t full = mapa_rank(smem_u32(&bars[GB_FULL + s]), 0);
+          const bool second = kt >= nk1;
+          const CUtensorMap* mA = second ? &mapA2 : &mapA1;
+          const CUtensorMap* mB = second ? &mapB2 : &mapB1;
+          const int k0 = (second ? kt - nk1 : kt) * BK;
+          if (!a.a_mn) {
+            tma_load_2d_2sm(sa, mA, full, k0, m0);
+          } else {
+            tma_load_2d_2sm(sa, mA, full, m0, k0);
+            tma_load_2d_2sm(sa + 8192, mA, full, m0 + 64, k0);
+          }
+          if (!a.b_mn) {
+            tma_load_2d_2sm(sb, mB, full, k0, n0);
+          } else {
+            tma_load_2d_2sm(sb, mB, full, n0, k0);
+            tma_load_2d_2sm(sb + 8192, mB, full, n0 + 64, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============ MMA issuer: the leader CTA's warp 1 only ================================================================
+    if (rank == 0) {
+      const bool leader = elect_one_g();
+      const uint32_t idesc = make_idesc(256, BN, kFmtBF16, kFmtBF16, a.a_mn ? kMajorMN : kMajorK, a.b_mn ? kMajorMN : kMajorK);
+      const uint32_t a_lbo = a.a_mn ? 8192u : 16u, b_lbo = a.b_mn ? 8192u : 16u;
+      const uint32_t a_step = a.a_mn ? 128u : 2u, b_step = a.b_mn ? 128u : 2u;
+      uint32_t it = 0, tile_no = 0;
+      for (int t = pair; t < ntiles; t += npairs, ++tile_no) {
+        const uint32_t buf = tile_no & 1, aph = (tile_no >> 1) & 1;
+        mbar_wait(&bars[GB_ACC_EMPTY + buf], aph ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tb + buf * BN;
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+          const uint32_t s = it % kStages2, ph = (it / kStages2) & 1;
+          mbar_wait(&bars[GB_FULL + s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE2_BYTES);
+          const uint64_t dA = make_sdesc(sa, a_lbo, 1024), dB = make_sdesc(sa + A_BYTES, b_lbo, 1024);
+#pragma unroll
+          for (uint32_t k = 0; k < BK / 16; ++k)
+            if (leader) mma_ss_2sm(acc, dA + k * a_step, dB + k * b_step, idesc, (kt | (int)k) != 0);
+          if (leader) mma_commit_2sm(&bars[GB_EMPTY + s]);
+          __syncwarp();
+        }
+        if (leader) mma_commit_2sm(&bars[GB_ACC_FULL + buf]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============ epilogue (both CTAs): own 128 rows of the 256-row tile ==================================================
+    const int q = warp & 3, row = q * 32 + lane;
+    const bool issuer = warp == 2 && lane == 0;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    uint32_t tile_no = 0, slab_no = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++tile_no) {
+      int m0, n0;
+      coords(t, m0, n0);
+      m0 += 128 * (int)rank;
+      const uint32_t buf = tile_no & 1, aph = (tile_no >> 1) & 1;
+      if (lane == 0) mbar_wait(&bars[GB_ACC_FULL + buf], aph);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t acc = tmem_addr(tb, q * 32, buf * BN);
+      const int ncols = min(BN, a.N - n0);
+      const int slab_cols = a.out_f32 ? 32 : 64;
+      const int nslabs = (ncols + slab_cols - 1) / slab_cols;
+#pragma unroll 1
+      for (int sl = 0; sl < nslabs; ++sl, ++slab_no) {
+        uint8_t* slab = smem + G_EPI + (slab_no & 1) * SLAB_BYTES;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(acc + sl * slab_cols, v0);
+        if (!a.out_f32) tmem_ld32(acc + sl * slab_cols + 32, v1);
+        if (issuer) tma_store_wait_read<1>();
+        tmem_ld_wait();
+        if (sl == nslabs - 1) {   // accumulator buffer fully read: tell the leader's MMA warp (remote arrive from the peer CTA)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&bars[GB_ACC_EMPTY + buf]), 0));
+        }
+        named_bar(1, 128);
+        uint8_t* rowp = slab + row * 128;
+        if (a.out_f32) {
+#pragma unroll
+          for (uint32_t c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(rowp + ((c ^ rsw) << 4)) = make_uint4(v0[4 * c], v0[4 * c + 1], v0[4 * c + 2], v0[4 * c + 3]);
+        } else {
+#pragma unroll
+          for (uint32_t c = 0; c < 4; ++c) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(v0[8 * c + 0]), __uint_as_float(v0[8 * c + 1]));
+            o.y = pack_bf16(__uint_as_float(v0[8 * c + 2]), __uint_as_float(v0[8 * c + 3]));
+            o.z = pack_bf16(__uint_as_float(v0[8 * c + 4]), __uint_as_float(v0[8 * c + 5]));
+            o.w = pack_bf16(__uint_as_float(v0[8 * c + 6]), __uint_as_float(v0[8 * c + 7]));
+            *reinterpret_cast<uint4*>(rowp + ((c ^ rsw) << 4)) = o;
+            o.x = pack_bf16(__uint_as_float(v1[8 * c + 0]), __uint_as_float(v1[8 * c + 1]));
+            o.y = pack_bf16(__uint_as_float(v1[8 * c + 2]), __uint_as_float(v1[8 * c + 3]));
+            o.z = pack_bf16(__uint_as_float(v1[8 * c + 4]), __uint_as_float(v1[8 * c + 5]));
+            o.w = pack_bf16(__uint_as_float(v1[8 * c + 6]), __uint_as_float(v1[8 * c + 7]));
+            *reinterpret_cast<uint4*>(rowp + (((c + 4) ^ rsw) << 4)) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar(2, 128);
+        if (issuer && m0 < a.M) {
+          tma_store_2d(&mapC, slab, n0 + sl * slab_cols, m0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the pair may still use its shared memory / barriers
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+}
+
 // (M, K) operand: which dim is contiguous?  0 = K-major, 1 = MN-major, -1 = neither / misaligned
 int operand_major(const omni_tensor_t& t) {
   if (!present(t) || t.ndim != 2 || t.dtype != OMNI_BF16 || !aligned16(t.data)) return -1;
@@ -310,7 +544,22 @@ extern "C" int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream) {
   std::call_once(once[dev & 63], [] {
     cudaFuncSetAttribute(gemm_tc_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
     cudaFuncSetAttribute(gemm_tc_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
   });
+  // CTA pairs (256 x 256 tiles) when there are enough of them to fill the machine; g_gemm_mode (debug): 1 forces the
+  // 1-CTA kernel, 2 the 2-CTA kernel
+  const int64_t tiles2 = ((M + 255) / 256) * ((N + 255) / 256);
+  const bool pairs = !narrow && (g_gemm_mode == 2 || (g_gemm_mode == 0 && tiles2 >= sm_count()));
+  if (pairs) {
+    // both CTAs of a pair load 128-row boxes of B
+    if (int rc = operand_map(&mB1, B, bmaj, 128)) return rc;
+    if (K2 > 0) { if (int rc = operand_map(&mB2, p->b2, bmaj, 128)) return rc; } else { mB2 = mB1; }
+    a.tiles_n = (int)((N + 255) / 256);
+    const int grid2 = (int)std::min<int64_t>(2 * tiles2, (int64_t)(sm_count() & ~1));
+    gemm_tc2_kernel<<<grid2, kGemmThreads, G_SMEM, static_cast<cudaStream_t>(stream)>>>(mA1, mB1, mA2, mB2, mC, a);
+    OMNI_CUDA_LAUNCH_CHECK("gemm_tc2_kernel");
+    return OMNI_OK;
+  }
   const int64_t ntiles = (int64_t)a.tiles_m * a.tiles_n;
   const int grid = (int)std::min<int64_t>(ntiles, sm_count());
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -319,3 +568,5 @@ extern "C" int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream) {
   OMNI_CUDA_LAUNCH_CHECK("gemm_tc_kernel");
   return OMNI_OK;
 }
+
+extern "C" void omni_debug_set_gemm_mode(int mode) { omni::g_gemm_mode = mode; }

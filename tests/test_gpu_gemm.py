@@ -34,15 +34,23 @@ def _operand(rows, cols, seed, major, pad=0):
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 2048), (329, 8512, 2048), (1000, 2048, 4096), (90 * 329, 264, 200),
                                    (1, 8, 8), (130, 8, 2048), (64, 16384, 2048)])
 @pytest.mark.parametrize("amaj,bmaj", [("k", "k"), ("k", "mn"), ("mn", "mn"), ("mn", "k")])
-def test_gemm_matches_fp32_reference(M, N, K, amaj, bmaj):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gemm_matches_fp32_reference(M, N, K, amaj, bmaj, mode):
+    """mode 1: single-CTA 128 x 256 (or 128 x 64) tiles; mode 2: CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles) for
+    every shape they are legal for - ragged M / N / K, all four operand-major combinations."""
     from omnimamba_b200 import _cabi
     a, ad = _operand(M, K, 1, amaj, pad=8)
     b, bd = _operand(N, K, 2, bmaj, pad=16)
     ref = a.float() @ b.float().t()
     assert _cabi.gemm_operands_ok(ad, bd)
-    o32 = _cabi.gemm(ad, bd, torch.float32)
-    o16 = _cabi.gemm(ad, bd, torch.bfloat16)
-    torch.cuda.synchronize()
+    lib = _cabi.lib()
+    try:
+        lib.omni_debug_set_gemm_mode(mode)
+        o32 = _cabi.gemm(ad, bd, torch.float32)
+        o16 = _cabi.gemm(ad, bd, torch.bfloat16)
+        torch.cuda.synchronize()
+    finally:
+        lib.omni_debug_set_gemm_mode(0)
     e32 = rel_l2(o32, ref)
     ex = excess_over_rounding(o16, ref)
     print(f"gemm M={M} N={N} K={K} {amaj}/{bmaj}: fp32-out rel_l2 {e32:.2e}, bf16-out excess {ex:.2e}, plain {rel_l2(o16, ref):.2e}")
@@ -58,11 +66,17 @@ def test_gemm_second_operand_pair_is_lora():
     x, w = _rand((M, K), 3), _rand((N, K), 4, 0.02)
     t, bl = _rand((M, r), 5), _rand((N, r), 6, 0.1)
     ref = x.float() @ w.float().t() + t.float() @ bl.float().t()
-    out = _cabi.gemm(x.to(DEV), w.to(DEV), torch.float32, t.to(DEV), bl.to(DEV))
-    torch.cuda.synchronize()
-    e = rel_l2(out, ref)
-    print(f"gemm + LoRA pair: {e:.2e}")
-    assert e <= 1e-5, e
+    lib = _cabi.lib()
+    for mode in (1, 2):
+        try:
+            lib.omni_debug_set_gemm_mode(mode)
+            out = _cabi.gemm(x.to(DEV), w.to(DEV), torch.float32, t.to(DEV), bl.to(DEV))
+            torch.cuda.synchronize()
+        finally:
+            lib.omni_debug_set_gemm_mode(0)
+        e = rel_l2(out, ref)
+        print(f"gemm + LoRA pair (tile mode {mode}): {e:.2e}")
+        assert e <= 1e-5, e
 
 
 def test_linear_autograd_matches_torch():
