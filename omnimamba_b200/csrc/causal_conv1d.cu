@@ -513,7 +513,11 @@ bool try_launch_bwd_fast(const ConvArgs& a, int W, const omni_tensor_t& x, const
     // enough work to fill the GPU (4x fewer partial-sum atomics), else 64 (L = 329, the stage-1 training length, with 256:
     // one segment of 256 tokens, one of 73 and idle ones - the kernel ran at 20 % of the HBM roofline there)
     const int64_t cols = (a.D + 127) / 128;
-    const int tl = (a.L >= kSegs * 256 && cols * a.B * ((a.L + kSegs * 256 - 1) / (kSegs * 256)) >= 4 * (int64_t)sm_count()) ? 256 : 64;
+    int tl = (a.L >= kSegs * 256 && cols * a.B * ((a.L + kSegs * 256 - 1) / (kSegs * 256)) >= 4 * (int64_t)sm_count()) ? 256 : 64;
+    if (tl == 64) {  // even segments: every warp of every block gets the same share (L = 329: 8 x 42 instead of 5 x 64 + 9)
+      const int nblk = (a.L + kSegs * 64 - 1) / (kSegs * 64);
+      tl = (a.L + kSegs * nblk - 1) / (kSegs * nblk);
+    }
     dim3 block(32, kSegs), grid((unsigned)cols, (a.L + kSegs * tl - 1) / (kSegs * tl), a.B);
     if (a.silu) conv1d_bwd_fast_kernel<T, true><<<grid, block, 0, s>>>(a, tl);
     else conv1d_bwd_fast_kernel<T, false><<<grid, block, 0, s>>>(a, tl);

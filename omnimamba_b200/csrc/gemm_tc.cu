@@ -72,7 +72,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
                const __grid_constant__ CUtensorMap mapC, GemmArgs a) {
   constexpr uint32_t B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr uint32_t kAccStride = BN < 32 ? 32 : BN;   // (the epilogue reads 32 columns at a time)
+  constexpr uint32_t kTmemCols = 2 * kAccStride;
   static_assert(kStages * STAGE_BYTES <= G_EPI && kStages <= kMaxStages, "stage ring");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_BAR);
@@ -148,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       const uint32_t buf = tile_no & 1, aph = (tile_no >> 1) & 1;
       mbar_wait(&bars[GB_ACC_EMPTY + buf], aph ^ 1);
       tc_fence_after();
-      const uint32_t acc = tb + buf * BN;
+      const uint32_t acc = tb + buf * kAccStride;
       for (int kt = 0; kt < nk; ++kt, ++it) {
         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
         mbar_wait(&bars[GB_FULL + s], ph);
@@ -177,7 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       if (lane == 0) mbar_wait(&bars[GB_ACC_FULL + buf], aph);
       __syncwarp();
       tc_fence_after();
-      const uint32_t acc = tmem_addr(tb, q * 32, buf * BN);
+      const uint32_t acc = tmem_addr(tb, q * 32, buf * kAccStride);
       const int ncols = min(BN, a.N - n0);
       const int slab_cols = a.out_f32 ? 32 : 64;
       const int nslabs = (ncols + slab_cols - 1) / slab_cols;
@@ -186,7 +187,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         uint8_t* slab = smem + G_EPI + (slab_no & 1) * SLAB_BYTES;
         uint32_t v0[32], v1[32];
         tmem_ld32(acc + sl * slab_cols, v0);
-        if (!a.out_f32) tmem_ld32(acc + sl * slab_cols + 32, v1);
+        if (BN > 32 && !a.out_f32) tmem_ld32(acc + sl * slab_cols + 32, v1);   // (BN <= 32: columns 32.. of the slab are clipped by the store)
+        else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v1[e] = 0u;
+        }
         if (issuer) tma_store_wait_read<1>();   // the store issued two slabs ago has read this buffer
         tmem_ld_wait();
         if (sl == nslabs - 1) {                 // accumulator buffer fully read: hand it back to the MMA warp
@@ -517,7 +522,10 @@ extern "C" int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream) {
   // too few 128 x 256 tiles to occupy the SMs (decode: M = batch): 128 x 64 tiles, four times as many CTAs stream the weights
   const int64_t tiles_m = (M + BM - 1) / BM;
   const bool narrow = tiles_m * ((N + 255) / 256) * 2 <= sm_count() && N > 64;
-  const int BN = narrow ? 64 : 256;
+  // N <= 16 (the rank-r LoRA GEMMs): 128 x 16 tiles - a 256-wide tile would spend 16 x the tensor time and stage 32 KB of
+  // zeros per K step; needs a K-major b (its MN-major form would be 16-byte rows)
+  const bool tiny_n = N <= 16 && bmaj == 0 && (K2 == 0);
+  const int BN = tiny_n ? 16 : (narrow ? 64 : 256);
   CUtensorMap mA1, mB1, mA2, mB2, mC;
   if (int rc = operand_map(&mA1, A, amaj, BM)) return rc;
   if (int rc = operand_map(&mB1, B, bmaj, BN)) return rc;
@@ -544,12 +552,13 @@ extern "C" int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream) {
   std::call_once(once[dev & 63], [] {
     cudaFuncSetAttribute(gemm_tc_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
     cudaFuncSetAttribute(gemm_tc_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    cudaFuncSetAttribute(gemm_tc_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
     cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
   });
   // CTA pairs (256 x 256 tiles) when there are enough of them to fill the machine; g_gemm_mode (debug): 1 forces the
   // 1-CTA kernel, 2 the 2-CTA kernel
   const int64_t tiles2 = ((M + 255) / 256) * ((N + 255) / 256);
-  const bool pairs = !narrow && (g_gemm_mode == 2 || (g_gemm_mode == 0 && tiles2 >= sm_count()));
+  const bool pairs = !narrow && !tiny_n && (g_gemm_mode == 2 || (g_gemm_mode == 0 && tiles2 >= sm_count()));
   if (pairs) {
     // both CTAs of a pair load 128-row boxes of B
     if (int rc = operand_map(&mB1, B, bmaj, 128)) return rc;
@@ -563,7 +572,8 @@ extern "C" int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream) {
   const int64_t ntiles = (int64_t)a.tiles_m * a.tiles_n;
   const int grid = (int)std::min<int64_t>(ntiles, sm_count());
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (narrow) gemm_tc_kernel<64, 8><<<grid, kGemmThreads, G_SMEM, s>>>(mA1, mB1, mA2, mB2, mC, a);
+  if (tiny_n) gemm_tc_kernel<16, 8><<<grid, kGemmThreads, G_SMEM, s>>>(mA1, mB1, mA2, mB2, mC, a);
+  else if (narrow) gemm_tc_kernel<64, 8><<<grid, kGemmThreads, G_SMEM, s>>>(mA1, mB1, mA2, mB2, mC, a);
   else gemm_tc_kernel<256, 4><<<grid, kGemmThreads, G_SMEM, s>>>(mA1, mB1, mA2, mB2, mC, a);
   OMNI_CUDA_LAUNCH_CHECK("gemm_tc_kernel");
   return OMNI_OK;

@@ -41,6 +41,14 @@ def mm_nt(a, b, out_dtype=None, a2=None, b2=None):
     return r if out_dtype is None else r.to(out_dtype)
 
 
+def _small_t(t2):
+    """(M, r) -> its transpose (r, M) as a K-major operand whose row pitch is a multiple of 8 elements (TMA: 16-byte strides)."""
+    M, r = t2.shape
+    buf = t2.new_empty(r, (M + 7) // 8 * 8)
+    buf[:, :M] = t2.t()
+    return buf[:, :M]
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x w^T (+ x2 w2^T) (+ bias); forward, dgrad and wgrad all run on the same GEMM kernel."""
 
@@ -68,10 +76,12 @@ class _LinearFn(torch.autograd.Function):
             dw = mm_nt(dy2.t(), x.reshape(-1, x.shape[-1]).t())                    # (N, M) @ (M, K)
         if ctx.has_bias and need[2]:
             db = dy2.sum(0)
+        # (rank-r operands: their transposed views have 16-byte rows; contiguous copies are a few hundred KB and let the
+        # GEMM use its 128 x 16 tile instead of a 256-wide one)
         if x2 is not None and need[3]:
-            dx2 = mm_nt(dy2, w2.t()).view(x2.shape)
+            dx2 = mm_nt(dy2, w2.t().contiguous()).view(x2.shape)
         if w2 is not None and need[4]:
-            dw2 = mm_nt(dy2.t(), x2.reshape(-1, x2.shape[-1]).t())
+            dw2 = mm_nt(dy2.t(), _small_t(x2.reshape(-1, x2.shape[-1])))
         return dx, dw, db, dx2, dw2
 
 
