@@ -12,7 +12,13 @@ def load_config_hf(model_name):
 
 
 def load_state_dict_hf(model_name, device=None, dtype=None):
-    sd = torch.load(os.path.join(model_name, "pytorch_model.bin"), map_location="cpu")
+    """`model_name` is a local directory holding `model.safetensors` or `pytorch_model.bin` (tensors only: weights_only)."""
+    st = os.path.join(model_name, "model.safetensors")
+    if os.path.exists(st):
+        from safetensors.torch import load_file   # (ships with transformers)
+        sd = load_file(st, device="cpu")
+    else:
+        sd = torch.load(os.path.join(model_name, "pytorch_model.bin"), map_location="cpu", weights_only=True)
     if dtype is not None:
         sd = {k: v.to(dtype=dtype) for k, v in sd.items()}
     return {k: v.to(device=device) for k, v in sd.items()}

@@ -16,7 +16,13 @@ from .causal_conv1d import conv1d_bwd_raw, conv1d_fwd_raw
 from .gemm import mm_nt
 from .layernorm_gated import norm_gated_bwd_raw, norm_gated_fwd_raw
 
+import os
+
 _ALGO = {"auto": abi.SSD_AUTO, "recurrent": abi.SSD_RECURRENT, "chunked_tc": abi.SSD_CHUNKED_TC}
+# Process-wide opt-out of the fp16-operand tensor-core scan ("Numerical range"): OMNI_SSD_ALGO=recurrent makes
+# every "auto" call - mamba_chunk_scan_combined, mamba_split_conv1d_scan_combined, Mamba2 - take the exact fp32 recurrence.
+_DEFAULT_ALGO = os.environ.get("OMNI_SSD_ALGO", "auto")
+assert _DEFAULT_ALGO in _ALGO, f"OMNI_SSD_ALGO must be one of {sorted(_ALGO)}"
 
 
 def _last_contig(t):
@@ -42,7 +48,7 @@ def ssd_fwd_raw(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initia
     p.workspace = abi.tdesc(ws)
     p.chunk_size, p.dt_softplus = int(chunk_size), int(bool(dt_softplus))
     p.dt_min, p.dt_max = float(dt_limit[0]), float(min(dt_limit[1], 3.0e38))
-    p.algo = _ALGO[algo]
+    p.algo = _ALGO[_DEFAULT_ALGO if algo == "auto" else algo]
     abi.call("omni_ssd_chunk_scan_fwd", p, x.device)
     return out, fin
 
@@ -72,6 +78,8 @@ def ssd_bwd_raw(dout, x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, 
             all(t.shape[d] == 1 or t.stride(d) % 8 == 0 for d in range(t.dim() - 1))
 
     tc_bytes = 0
+    if algo == "auto":
+        algo = _DEFAULT_ALGO
     if (algo != "recurrent" and z is None and seq_idx is None and (D is None or D.dim() == 1)
             and (nheads // ngroups) % 2 == 0 and all(_tma_ok(t) for t in (x, dout, dx, B, C))):
         tc_bytes = abi.ssd_bwd_tc_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate)
@@ -240,7 +248,7 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
         p.xbc_conv, p.scan_out, p.rstd, p.y, p.out = (abi.tdesc(t) for t in (xBC_conv, scan_out, rstd, y, out))
         p.final_states, p.workspace = abi.tdesc(fin), abi.tdesc(ws)
         p.nheads, p.headdim, p.ngroups, p.dstate, p.chunk_size = nheads, headdim, ngroups, dstate, int(chunk_size)
-        p.activation, p.norm_before_gate, p.algo = act, int(bool(norm_before_gate)), abi.SSD_AUTO
+        p.activation, p.norm_before_gate, p.algo = act, int(bool(norm_before_gate)), _ALGO[_DEFAULT_ALGO]
         p.dt_min, p.dt_max, p.rmsnorm_eps = float(dt_limit[0]), float(min(dt_limit[1], 3.0e38)), float(rmsnorm_eps)
         abi.call("omni_split_conv1d_scan_fwd", p, dev)     # conv1d + SiLU -> scan -> gated norm (-> out_proj): one C-ABI call
         scan_out = scan_out.view(batch, seqlen, nheads, headdim)
