@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OMNI_ABI_VERSION 4
+#define OMNI_ABI_VERSION 5
 #if defined(__GNUC__)
 #define OMNI_API __attribute__((visibility("default")))
 #else
@@ -122,6 +122,9 @@ typedef struct omni_ssd_fwd_params {
   float dt_min, dt_max; /* dt_limit */
   int32_t algo;         /* omni_ssd_algo_t */
 } omni_ssd_fwd_params_t;
+/* 1 when the call would run on the tcgen05 kernels for exactly these params (algo AUTO falls back to the exact fp32
+ * recurrence otherwise) - the single eligibility test; callers ask instead of re-deriving it. */
+OMNI_API int omni_ssd_fwd_tc_supported(const omni_ssd_fwd_params_t* p);
 OMNI_API int64_t omni_ssd_fwd_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim,
                                               int64_t ngroups, int64_t dstate);
 OMNI_API int omni_ssd_chunk_scan_fwd(const omni_ssd_fwd_params_t* p, void* stream);
@@ -149,6 +152,7 @@ OMNI_API int64_t omni_ssd_bwd_workspace_elems(int64_t batch, int64_t seqlen, int
 OMNI_API int64_t omni_ssd_bwd_tc_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim,
                                                  int64_t ngroups, int64_t dstate);
 OMNI_API int omni_ssd_chunk_scan_bwd(const omni_ssd_bwd_params_t* p, void* stream);
+OMNI_API int omni_ssd_bwd_tc_supported(const omni_ssd_bwd_params_t* p); /* as omni_ssd_fwd_tc_supported, for the backward */
 
 /* ---- gated RMSNorm / LayerNorm ------------------------------------------------------------ */
 /* rmsnorm_fn / layernorm_fn(x, weight, bias, z, eps, group_size, norm_before_gate)

@@ -139,7 +139,7 @@ ENTRY_POINTS = {
     "omni_softmax_ce_bwd": SoftmaxCe,
 }
 OTHER_SYMBOLS = ["omni_version", "omni_last_error", "omni_launch_count", "omni_reset_launch_count",
-                 "omni_ssd_bwd_workspace_elems", "omni_selective_scan_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint", "omni_debug_set_bwd_trace", "omni_debug_set_handoff", "omni_gemm_bf16_supported", "omni_debug_set_gemm_mode"]
+                 "omni_ssd_bwd_workspace_elems", "omni_selective_scan_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint", "omni_debug_set_bwd_trace", "omni_debug_set_handoff", "omni_gemm_bf16_supported", "omni_debug_set_gemm_mode", "omni_ssd_bwd_tc_supported", "omni_ssd_fwd_tc_supported"]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libomnissm.so")
 _lib: Optional[C.CDLL] = None
@@ -178,6 +178,10 @@ def lib() -> C.CDLL:
     l.omni_debug_tmem_bench.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     l.omni_debug_tmem_bench.restype = C.c_int
     l.omni_gemm_bf16_supported.restype = C.c_int
+    l.omni_ssd_bwd_tc_supported.argtypes = [C.POINTER(SsdBwd)]
+    l.omni_ssd_bwd_tc_supported.restype = C.c_int
+    l.omni_ssd_fwd_tc_supported.argtypes = [C.POINTER(SsdFwd)]
+    l.omni_ssd_fwd_tc_supported.restype = C.c_int
     l.omni_debug_set_gemm_mode.argtypes = [C.c_int]
     l.omni_debug_set_gemm_mode.restype = None
     l.omni_debug_set_handoff.argtypes = [C.c_uint, C.c_int]

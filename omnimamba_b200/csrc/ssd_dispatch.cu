@@ -47,3 +47,8 @@ extern "C" int64_t omni_ssd_bwd_tc_workspace_bytes(int64_t batch, int64_t seqlen
   if (headdim != 64 || dstate != 128) return 0;
   return ssd_tc_bwd_workspace_bytes(batch, seqlen, nheads, ngroups);
 }
+
+// 1 when omni_ssd_chunk_scan_bwd would take the tensor-core path for exactly these params (dtypes, strides, alignment,
+// workspace size, driver support): the ONE eligibility test - the Python surface asks instead of re-deriving it.
+extern "C" int omni_ssd_bwd_tc_supported(const omni_ssd_bwd_params_t* p) { return p != nullptr && ssd_tc_bwd_supported(p) ? 1 : 0; }
+extern "C" int omni_ssd_fwd_tc_supported(const omni_ssd_fwd_params_t* p) { return p != nullptr && ssd_tc_fwd_supported(p) ? 1 : 0; }

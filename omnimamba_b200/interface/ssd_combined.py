@@ -73,26 +73,8 @@ def ssd_bwd_raw(dout, x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, 
     ddtb_part = torch.empty(batch, nheads, device=dev, dtype=torch.float32)
     dD_part = torch.empty(batch, nheads, headdim, device=dev, dtype=torch.float32)
     dinit = torch.empty(batch, nheads, headdim, dstate, device=dev, dtype=torch.float32) if want_dinitial else None
-    def _tma_ok(t):  # 16-byte aligned base and outer strides, contiguous rows
-        return t.dtype == torch.bfloat16 and t.stride(-1) == 1 and t.data_ptr() % 16 == 0 and \
-            all(t.shape[d] == 1 or t.stride(d) % 8 == 0 for d in range(t.dim() - 1))
-
-    tc_bytes = 0
     if algo == "auto":
         algo = _DEFAULT_ALGO
-    if (algo != "recurrent" and z is None and seq_idx is None and (D is None or D.dim() == 1)
-            and (nheads // ngroups) % 2 == 0 and all(_tma_ok(t) for t in (x, dout, dx, B, C))):
-        tc_bytes = abi.ssd_bwd_tc_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate)
-    if algo == "chunked_tc" and tc_bytes == 0:
-        raise RuntimeError("ssd bwd: algo='chunked_tc' needs bf16 x/B/C/dout (16-byte aligned rows), headdim 64, "
-                           "d_state 128, an even number of heads per group, D of shape (H), no z / seq_idx")
-    if tc_bytes > 0:  # tensor-core path: fp16 B/C copies + fp16 chunk states and state gradients (not zero-filled)
-        ws = torch.empty((tc_bytes + 3) // 4, device=dev, dtype=torch.float32)
-        dD_part = torch.empty(batch, nheads, device=dev, dtype=torch.float32)
-        algo = "chunked_tc"
-    else:
-        ws = torch.zeros(abi.ssd_bwd_workspace_elems(batch, seqlen, nheads, headdim, dstate), device=dev, dtype=torch.float32)
-        algo = "recurrent"
     p = abi.SsdBwd()
     p.x, p.dt, p.A, p.B, p.C = (abi.tdesc(t) for t in (x, dt, A, B, C))
     p.D, p.z, p.dt_bias = abi.tdesc(D), abi.tdesc(z), abi.tdesc(dt_bias)
@@ -101,11 +83,28 @@ def ssd_bwd_raw(dout, x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, 
     p.dout, p.dfinal_states = abi.tdesc(dout), abi.tdesc(dfinal_states)
     p.dx, p.ddt, p.dB, p.dC, p.dz = (abi.tdesc(t) for t in (dx, ddt, dB, dC, dz))
     p.dinitial_states = abi.tdesc(dinit)
-    p.dA_part, p.ddt_bias_part, p.dD_part = abi.tdesc(dA_part), abi.tdesc(ddtb_part), abi.tdesc(dD_part)
-    p.workspace = abi.tdesc(ws)
+    p.dA_part, p.ddt_bias_part = abi.tdesc(dA_part), abi.tdesc(ddtb_part)
     p.chunk_size, p.dt_softplus = int(chunk_size), int(bool(dt_softplus))
     p.dt_min, p.dt_max = float(dt_limit[0]), float(min(dt_limit[1], 3.0e38))
-    p.algo = _ALGO[algo]
+    # Tensor-core path?  The library decides (omni_ssd_bwd_tc_supported: ONE eligibility test for dtypes, strides, alignment,
+    # geometry, driver) on the params it would be called with: the tensor-core workspace and dD layout are offered first.
+    use_tc = False
+    if algo != "recurrent" and x.dtype == torch.bfloat16:
+        tc_bytes = abi.ssd_bwd_tc_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate)
+        if tc_bytes > 0:
+            ws = torch.empty((tc_bytes + 3) // 4, device=dev, dtype=torch.float32)   # fp16 B / C copies, chunk states (not zero-filled)
+            dD_tc = torch.empty(batch, nheads, device=dev, dtype=torch.float32)
+            p.dD_part, p.workspace = abi.tdesc(dD_tc), abi.tdesc(ws)
+            use_tc = bool(abi.lib().omni_ssd_bwd_tc_supported(abi.C.byref(p)))
+            if use_tc:
+                dD_part = dD_tc
+    if algo == "chunked_tc" and not use_tc:
+        raise RuntimeError("ssd bwd: algo='chunked_tc' needs bf16 x/B/C/dout (16-byte aligned rows), headdim 64, "
+                           "d_state 128, an even number of heads per group, D of shape (H), no z / seq_idx")
+    if not use_tc:
+        ws = torch.zeros(abi.ssd_bwd_workspace_elems(batch, seqlen, nheads, headdim, dstate), device=dev, dtype=torch.float32)
+        p.dD_part, p.workspace = abi.tdesc(dD_part), abi.tdesc(ws)
+    p.algo = _ALGO["chunked_tc" if use_tc else "recurrent"]
     abi.call("omni_ssd_chunk_scan_bwd", p, dev)
     dA = dA_part.sum(0)
     ddt_bias = ddtb_part.sum(0) if dt_bias is not None else None
