@@ -65,12 +65,31 @@ def model_fwd(device, steps=5, warmup=3, batch=8, seqlen=1024, n_layer=N_LAYER):
     _cabi.reset_launch_count()
     y = step()
     launches = _cabi.launch_count()
-    ms = _events_ms(step, steps, warmup, False)
+    ms_eager = _events_ms(step, steps, warmup, False)
+    # the same forward replayed from a CUDA graph (static input; every libomnissm call is capturable): removes the host-side
+    # launch gaps between ~670 kernels
+    ms = ms_eager
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            yg = step()
+        ms_graph = _events_ms(graph.replay, steps, warmup, False)
+        same = bool(torch.equal(yg, y))
+        if same and ms_graph < ms_eager:
+            ms = ms_graph
+    except Exception as e:  # noqa: BLE001
+        ms_graph, same = None, f"{type(e).__name__}: {e}"[:200]
     toks = batch * seqlen
     flops = _gemm_flops_per_token() * toks * n_layer / N_LAYER
     del stack
     return {"workload": f"config 2: {n_layer}-layer d_model={D_MODEL} forward, B={batch} L={seqlen}, bf16 autocast, LoRA in_proj",
-            "value": toks / ms * 1e3, "unit": "tokens/s", "ms_per_step": ms, "libomnissm_launches_per_step": launches,
+            "value": toks / ms * 1e3, "unit": "tokens/s", "ms_per_step": ms, "ms_per_step_eager": ms_eager,
+            "ms_per_step_cuda_graph": ms_graph, "graph_output_bit_equal": same, "libomnissm_launches_per_step": launches,
             "gemm_tflops_achieved": flops / ms / 1e9, "finite": bool(torch.isfinite(y.float()).all().item())}
 
 

@@ -20,6 +20,27 @@ def _autocast_dtype(device_type="cuda"):
     return torch.get_autocast_dtype(device_type) if torch.is_autocast_enabled(device_type) else None
 
 
+_CAST_CACHE = {}
+
+
+def cast_param(w, dtype):
+    """w.to(dtype) for a GEMM operand.  FROZEN parameters (stage "align": every base weight of the backbone) keep their
+    low-precision copy across calls - autocast's own weight cache does the same inside one context, but the custom GEMM path
+    casts by hand, and re-casting 26 M weights per layer and step is 4 launches and ~100 MB of traffic for nothing.
+    Keyed on the parameter object and its version counter, so an in-place update (optimizer, load_state_dict) refreshes it."""
+    if w is None or w.dtype == dtype:
+        return w
+    if w.requires_grad or not isinstance(w, torch.nn.Parameter):
+        return w.to(dtype)
+    key = (id(w), dtype)
+    hit = _CAST_CACHE.get(key)
+    if hit is not None and hit[0] is w and hit[1] == w._version and hit[2].device == w.device:
+        return hit[2]
+    c = w.detach().to(dtype)
+    _CAST_CACHE[key] = (w, w._version, c)
+    return c
+
+
 def gemm_tc_available() -> bool:
     return _BACKEND == "tc" and hasattr(abi, "gemm") and abi.gemm_supported()
 
@@ -89,7 +110,7 @@ def linear(x, w, bias=None):
     """F.linear with autocast semantics; bf16 CUDA operands run on the tcgen05 GEMM."""
     ac = _autocast_dtype(x.device.type) if x.is_cuda else None
     if ac is not None:
-        x, w = x.to(ac), w.to(ac)
+        x, w = x.to(ac), cast_param(w, ac)
         bias = bias.to(ac) if bias is not None else None
     if not _eligible(x, w):
         return F.linear(x, w, bias)
@@ -103,7 +124,8 @@ def lora_linear(x, w, bias, lora_a, lora_b, scaling, dropout=None):
     xd = dropout(x) if dropout is not None else x
     ac = _autocast_dtype(x.device.type) if x.is_cuda else None
     if ac is not None:
-        x, xd, w, lora_a, lora_b = (t.to(ac) for t in (x, xd, w, lora_a, lora_b))
+        x, xd = x.to(ac), xd.to(ac)
+        w, lora_a, lora_b = cast_param(w, ac), cast_param(lora_a, ac), cast_param(lora_b, ac)
         bias = bias.to(ac) if bias is not None else None
     if not _eligible(x, w, lora_a, lora_b):
         return F.linear(x, w, bias) + F.linear(F.linear(xd, lora_a), lora_b) * scaling

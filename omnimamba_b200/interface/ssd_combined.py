@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from .. import _cabi as abi
 from .causal_conv1d import conv1d_bwd_raw, conv1d_fwd_raw
-from .gemm import mm_nt
+from .gemm import cast_param, mm_nt
 from .layernorm_gated import norm_gated_bwd_raw, norm_gated_fwd_raw
 
 import os
@@ -232,7 +232,7 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
         ac = _autocast_dtype()
         w, b_ = outproj_weight, outproj_bias
         if w is not None and ac is not None:
-            w = w.to(ac)
+            w = cast_param(w, ac)
             b_ = b_.to(ac) if b_ is not None else None
         fuse_gemm = (w is not None and w.dtype == torch.bfloat16 and dt_ == torch.bfloat16 and w.stride(-1) == 1
                      and w.stride(0) % 8 == 0 and w.data_ptr() % 16 == 0 and w.shape[0] % 8 == 0 and abi.gemm_supported())
@@ -307,7 +307,7 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
             dout2 = dout.reshape(M, dout.shape[-1])
             if dout2.stride(-1) != 1 and dout2.stride(0) != 1:
                 dout2 = dout2.contiguous()
-            dy = mm_nt(dout2, outproj_weight.to(dout2.dtype).t())
+            dy = mm_nt(dout2, cast_param(outproj_weight, dout2.dtype).t())
             doutproj_bias = dout2.sum(0).to(outproj_bias.dtype) if outproj_bias is not None else None
         else:
             dy = dout.reshape(M, dim)

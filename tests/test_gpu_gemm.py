@@ -32,7 +32,7 @@ def _operand(rows, cols, seed, major, pad=0):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 2048), (329, 8512, 2048), (1000, 2048, 4096), (90 * 329, 264, 200),
-                                   (1, 8, 8), (130, 8, 2048), (64, 16384, 2048)])
+                                   (1, 8, 8), (130, 8, 2048), (64, 16384, 2048), (64, 8512, 2048), (3, 2048, 4096)])
 @pytest.mark.parametrize("amaj,bmaj", [("k", "k"), ("k", "mn"), ("mn", "mn"), ("mn", "k")])
 @pytest.mark.parametrize("mode", [1, 2])
 def test_gemm_matches_fp32_reference(M, N, K, amaj, bmaj, mode):
