@@ -141,7 +141,9 @@ ENTRY_POINTS = {
 OTHER_SYMBOLS = ["omni_version", "omni_last_error", "omni_launch_count", "omni_reset_launch_count",
                  "omni_ssd_bwd_workspace_elems", "omni_selective_scan_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint", "omni_debug_set_bwd_trace", "omni_debug_set_handoff", "omni_gemm_bf16_supported", "omni_debug_set_gemm_mode", "omni_ssd_bwd_tc_supported", "omni_ssd_fwd_tc_supported"]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libomnissm.so")
+# OMNI_LIB_PATH: A/B experiments only (a second build of the same library, e.g. scripts/ab_build.sh); the product path is
+# the in-tree lib/libomnissm.so
+LIB_PATH = os.environ.get("OMNI_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libomnissm.so")
 _lib: Optional[C.CDLL] = None
 
 

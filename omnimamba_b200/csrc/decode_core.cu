@@ -58,9 +58,21 @@ template <> __device__ __forceinline__ uint2 pack4<__half>(const float (&o)[4]) 
   return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
 }
 
+#ifndef OMNI_DEC_OCC
+#define OMNI_DEC_OCC 4     // CTAs per SM the register budget is cut for (4 x 256 threads x 64 registers)
+#endif
+#ifndef OMNI_DEC_ROWS16
+#define OMNI_DEC_ROWS16 8   // state rows per warp step for a 16-bit state (fp32: half of it)
+#endif
+// Occupancy: 64 sequences x 8 CTAs = 512 CTAs.  At 2 CTAs per SM (the 32-row steps of the first version: 128 registers) they
+// run as 1.73 waves on 296 slots - two wave times for 1.73 waves of work - and every CTA's conv phase / cluster barriers /
+// norm phase leave its slot's share of the HBM stream idle.  At 64 registers four CTAs fit per SM: ALL 512 CTAs are resident
+// at once (592 slots), there is no second wave, and the phases of one CTA hide behind the state streams of the three others.
+// Measured at batch 64, bf16 state (scripts/bench_decode_core.py, same box): 2 CTAs x 32-row steps 38.0 us, 3 x 16 47.0, 4 x 16
+// 41.2 (spills), 4 x 8 33.1, 4 x 4 33.6, 5 x 8 38.2 (spills), 5 x 4 34.4, 6 x 4 35.6;  fp32 state: 59.4 -> 55.7 us.
 template <typename TS>
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads) mamba2_decode_core_kernel(DecArgs a) {
-  constexpr int R = sizeof(TS) == 4 ? 16 : 32;   // state rows per warp step: 8 KB in flight per warp (16-row steps for a 16-bit state: 39.2 us instead of 37.6, measured)
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads, OMNI_DEC_OCC) mamba2_decode_core_kernel(DecArgs a) {
+  constexpr int R = sizeof(TS) == 4 ? OMNI_DEC_ROWS16 / 2 : OMNI_DEC_ROWS16;   // state rows per warp step
   using Raw = typename Raw4<TS>::type;
   cg::cluster_group cluster = cg::this_cluster();
   const int cr = (int)cluster.block_rank();           // 8 heads of the sequence
@@ -69,6 +81,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads) 
   const int dim = a.H * kP, conv_dim = dim + 2 * kN;
   __shared__ float xs[kHeadsPerCta * kP], Bs[kN], Cs[kN], ys[kHeadsPerCta * kP], red[32];
   __shared__ float part;
+
+  // (the first step's state rows do not depend on anything computed here: requested before the conv phase, they arrive
+  // while it and the first cluster barrier run)
+  const int h_w = cr * kHeadsPerCta + warp;
+  TS* const sbase = static_cast<TS*>(a.state) + (int64_t)b * a.st_b + (int64_t)h_w * a.st_h + lane * 4;
+  Raw raw[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) raw[r] = *reinterpret_cast<const Raw*>(sbase + (int64_t)r * a.st_p);
 
   // ---- 1. conv-state update + SiLU: 2 x channels per thread (this CTA's heads) + 1 B/C channel per thread (all CTAs) ----
   const char* zrow = static_cast<const char*>(a.zx);
@@ -119,12 +139,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads) 
     float Bv[4], Cv[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) { Bv[e] = Bs[n + e] * dtv; Cv[e] = Cs[n + e]; }   // (dt folded into B: S += x_p (dt B))
-    TS* sbase = static_cast<TS*>(a.state) + (int64_t)b * a.st_b + (int64_t)h * a.st_h + n;
 #pragma unroll 1
     for (int p0 = 0; p0 < kP; p0 += R) {
-      Raw raw[R];
+      if (p0 > 0) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) raw[r] = *reinterpret_cast<const Raw*>(sbase + (int64_t)(p0 + r) * a.st_p);
+        for (int r = 0; r < R; ++r) raw[r] = *reinterpret_cast<const Raw*>(sbase + (int64_t)(p0 + r) * a.st_p);
+      }
       float acc[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -153,13 +173,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads) 
           }
         }
       }
+      // (R < 32: the butterfly stops with 32 / R lanes holding partial sums of the same row)
       float y = acc[0];
-      int row = lane;
-      if constexpr (R == 16) {
-        y += __shfl_xor_sync(0xffffffffu, y, 1);
-        row = lane >> 1;
-      }
-      if (R == 32 || (lane & 1) == 0) ys[warp * kP + p0 + row] = fmaf(xs[warp * kP + p0 + row], Dh, y);
+#pragma unroll
+      for (int off = 1; off < 32 / R; off <<= 1) y += __shfl_xor_sync(0xffffffffu, y, off);
+      const int row = lane / (32 / R);
+      if (lane % (32 / R) == 0) ys[warp * kP + p0 + row] = fmaf(xs[warp * kP + p0 + row], Dh, y);
     }
   }
   __syncthreads();

@@ -36,7 +36,8 @@ constexpr uint32_t SLAB_BYTES = 128 * 128;  // 128 rows x 128 B (64 bf16 or 32 f
 constexpr uint32_t G_EPI = 4 * (A_BYTES + 256 * BK * 2);   // = 8 * (A_BYTES + 64 * BK * 2): both shapes use 192 KB of stages
 constexpr uint32_t G_BAR = G_EPI + 2 * SLAB_BYTES;
 constexpr int kMaxStages = 8;
-int g_gemm_mode = 0;   // debug (omni_debug_set_gemm_mode): 0 auto, 1 single-CTA tiles only, 2 CTA pairs whenever the shape allows
+int g_gemm_mode = 0;   // debug (omni_debug_set_gemm_mode): 0 auto, 1 single-CTA tiles only, 2 CTA pairs whenever the shape allows,
+                       // 3 auto without the weight-streaming kernel of gemm_skinny.cu
 enum { GB_FULL = 0, GB_EMPTY = kMaxStages, GB_ACC_FULL = 2 * kMaxStages, GB_ACC_EMPTY = 2 * kMaxStages + 2, GB_COUNT = 2 * kMaxStages + 4 };
 constexpr uint32_t G_TMEMPTR = G_BAR + GB_COUNT * 8;
 constexpr uint32_t G_SMEM = G_TMEMPTR + 16;
@@ -494,6 +495,12 @@ int operand_map(CUtensorMap* m, const omni_tensor_t& t, int major, int rows_box)
 }  // namespace
 }  // namespace omni
 
+namespace omni {
+// gemm_skinny.cu: weight-streaming kernel for decode-shaped GEMMs (M <= 128 rows, K split over a cluster)
+bool gemm_skinny_eligible(int64_t M, int64_t N, int64_t K1, int64_t K2, int amaj, int bmaj);
+int gemm_skinny(const omni_gemm_params_t* p, cudaStream_t s);
+}  // namespace omni
+
 using namespace omni;
 
 extern "C" int omni_gemm_bf16_supported(void) { return get_encode_tiled() != nullptr ? 1 : 0; }
@@ -519,6 +526,10 @@ extern "C" int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream) {
   if (M == 0 || N == 0) return OMNI_OK;
   OMNI_CHECK(K1 > 0, OMNI_BAD_SHAPE, "gemm: K must be positive");
   OMNI_CHECK(M < (1ll << 31) && N < (1ll << 31) && K1 < (1ll << 31), OMNI_BAD_SHAPE, "gemm: dims must fit in 31 bits");
+  // decode-shaped (M = batch <= 128 rows of K-major operands): the weights are streamed once, K split over a cluster
+  // (g_gemm_mode 3, debug: keep such shapes on the tile kernels below)
+  if (g_gemm_mode != 3 && g_gemm_mode != 1 && gemm_skinny_eligible(M, N, K1, K2, amaj, bmaj))
+    return gemm_skinny(p, static_cast<cudaStream_t>(stream));
   // too few 128 x 256 tiles to occupy the SMs (decode: M = batch): 128 x 64 tiles, four times as many CTAs stream the weights
   const int64_t tiles_m = (M + BM - 1) / BM;
   const bool narrow = tiles_m * ((N + 255) / 256) * 2 <= sm_count() && N > 64;
@@ -579,4 +590,8 @@ extern "C" int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream) {
   return OMNI_OK;
 }
 
-extern "C" void omni_debug_set_gemm_mode(int mode) { omni::g_gemm_mode = mode; }
+namespace omni { extern int g_skinny_ksplit; }
+extern "C" void omni_debug_set_gemm_mode(int mode) {
+  if (mode >= 10) { omni::g_skinny_ksplit = mode - 10; return; }   // 10: automatic K split again; 11 / 12 / 14 / 18: forced
+  omni::g_gemm_mode = mode;
+}

@@ -59,6 +59,39 @@ def test_gemm_matches_fp32_reference(M, N, K, amaj, bmaj, mode):
     assert torch.equal(o16.cpu(), o32.cpu().to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("M", [1, 3, 64, 100, 128])
+@pytest.mark.parametrize("N,K,K2", [(8512, 2048, 0), (2048, 4096, 0), (8512, 2048, 8), (264, 1000, 0), (16384, 2048, 0), (1000, 520, 24)])
+def test_gemm_decode_shapes_stream_the_weights(M, N, K, K2):
+    """M = batch <= 128 rows of K-major operands take the weight-streaming kernel (csrc/gemm_skinny.cu: weight rows on the MMA
+    M dimension, K split over a thread-block cluster, partial tiles reduced through DSMEM): in_proj / out_proj of Mamba2.step
+    at d_model = 2048, ragged N / K, every cluster size (1, 2, 4, 8), with and without the LoRA pair - against fp32 PyTorch and
+    against the tile kernel of gemm_tc.cu on the same operands."""
+    from omnimamba_b200 import _cabi
+    x, w = _rand((M, K), 31), _rand((N, K), 32, 0.05)
+    ref = x.float() @ w.float().t()
+    extra = ()
+    if K2:
+        t, bl = _rand((M, K2), 33), _rand((N, K2), 34, 0.1)
+        ref = ref + t.float() @ bl.float().t()
+        extra = (t.to(DEV), bl.to(DEV))
+    xd, wd = x.to(DEV), w.to(DEV)
+    lib = _cabi.lib()
+    _cabi.reset_launch_count()
+    o32 = _cabi.gemm(xd, wd, torch.float32, *extra)
+    o16 = _cabi.gemm(xd, wd, torch.bfloat16, *extra)
+    try:
+        lib.omni_debug_set_gemm_mode(3)       # the same GEMM on the tile kernel
+        t32 = _cabi.gemm(xd, wd, torch.float32, *extra)
+    finally:
+        lib.omni_debug_set_gemm_mode(0)
+    torch.cuda.synchronize()
+    e32, ex = rel_l2(o32, ref), excess_over_rounding(o16, ref)
+    print(f"skinny gemm M={M} N={N} K={K} K2={K2}: fp32-out {e32:.2e}, bf16-out excess {ex:.2e}, vs tile kernel {rel_l2(o32, t32):.2e}")
+    assert e32 <= 1e-5 and ex <= 1e-4
+    assert rel_l2(o32, t32) <= 1e-5
+    assert torch.equal(o16.cpu(), o32.cpu().to(torch.bfloat16))
+
+
 def test_gemm_second_operand_pair_is_lora():
     """out = x W^T + t B^T in one accumulator (the LoRA branch of in_proj, lora.py:263-279): d_model=2048 -> 8512, r = 8."""
     from omnimamba_b200 import _cabi
