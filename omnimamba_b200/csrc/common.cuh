@@ -46,6 +46,35 @@ inline bool shape_is(const omni_tensor_t& t, int nd, int64_t a = -1, int64_t b =
 
 int sm_count();  // of the current device (cached per device)
 
+// Programmatic dependent launch (PDL) for the chains of small kernels of the decode step (add + norm -> in_proj -> layer core ->
+// out_proj, 192 launches per token): a kernel launched through launch_pdl may begin - launch latency, prologue, loads of
+// data no earlier kernel writes (weights, last step's states) - while its predecessor in the stream is still running;
+// it calls pdl_wait() before it touches anything a predecessor produces or still reads, and pdl_trigger() at its top so
+// that ITS successor may be scheduled in turn.  Works the same inside a captured CUDA graph (programmatic edges).
+// OMNI_PDL in the environment is a mask of the kernels that may start early (kPdl*); 0 launches everything fully serialised.
+enum { kPdlAddNorm = 1, kPdlGemm = 2, kPdlCore = 4, kPdlDefault = 3 };
+bool pdl_enabled(int kind);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              unsigned cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled(kind)) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // dispatch a lambda templated on the element type
 #define OMNI_DISPATCH_FLOAT(DT, T, ...)                                             \
   [&]() -> int {                                                                    \
@@ -60,6 +89,10 @@ int sm_count();  // of the current device (cached per device)
 // ---------------------------------------------------------------------------------------------
 // device side
 // ---------------------------------------------------------------------------------------------
+// PDL (see launch_pdl): both are no-ops in a kernel launched without the attribute
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }

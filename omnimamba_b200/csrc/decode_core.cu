@@ -82,14 +82,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads, 
   __shared__ float xs[kHeadsPerCta * kP], Bs[kN], Cs[kN], ys[kHeadsPerCta * kP], red[32];
   __shared__ float part;
 
-  // (the first step's state rows do not depend on anything computed here: requested before the conv phase, they arrive
-  // while it and the first cluster barrier run)
+  pdl_trigger();   // (PDL, common.cuh: out_proj may start streaming its weights while this kernel runs)
+  // (the first step's state rows do not depend on anything computed here - nor on in_proj, the previous kernel: the state
+  // was last written by this layer's own launch of the previous token - so they are requested before pdl_wait(), and arrive
+  // while the conv phase and the first cluster barrier run)
   const int h_w = cr * kHeadsPerCta + warp;
   TS* const sbase = static_cast<TS*>(a.state) + (int64_t)b * a.st_b + (int64_t)h_w * a.st_h + lane * 4;
   Raw raw[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) raw[r] = *reinterpret_cast<const Raw*>(sbase + (int64_t)r * a.st_p);
 
+  pdl_wait();      // zxbcdt comes from the previous kernel (in_proj)
   // ---- 1. conv-state update + SiLU: 2 x channels per thread (this CTA's heads) + 1 B/C channel per thread (all CTAs) ----
   const char* zrow = static_cast<const char*>(a.zx);
   auto zx_at = [&](int col) { return ld_any(a.zx, a.io_dtype, (int64_t)b * a.zx_b + col); };
@@ -251,10 +254,10 @@ extern "C" int omni_mamba2_decode_core(const omni_mamba2_decode_core_params_t* p
   a.eps = p->eps;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)(Bsz * kCluster);
-  switch (st.dtype) {
-    case OMNI_F32: mamba2_decode_core_kernel<float><<<grid, kDecThreads, 0, s>>>(a); break;
-    case OMNI_BF16: mamba2_decode_core_kernel<__nv_bfloat16><<<grid, kDecThreads, 0, s>>>(a); break;
-    default: mamba2_decode_core_kernel<__half><<<grid, kDecThreads, 0, s>>>(a); break;
+  switch (st.dtype) {   // (cluster dims are compile-time: __cluster_dims__)
+    case OMNI_F32: launch_pdl(kPdlCore, mamba2_decode_core_kernel<float>, dim3(grid), dim3(kDecThreads), 0, s, 1, a); break;
+    case OMNI_BF16: launch_pdl(kPdlCore, mamba2_decode_core_kernel<__nv_bfloat16>, dim3(grid), dim3(kDecThreads), 0, s, 1, a); break;
+    default: launch_pdl(kPdlCore, mamba2_decode_core_kernel<__half>, dim3(grid), dim3(kDecThreads), 0, s, 1, a); break;
   }
   OMNI_CUDA_LAUNCH_CHECK("mamba2_decode_core_kernel");
   return OMNI_OK;

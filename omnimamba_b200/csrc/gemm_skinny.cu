@@ -134,22 +134,33 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = *tmem_ptr;
+  pdl_trigger();
 
   if (warp == 0) {
     // ============ TMA producer ==========================================================================================
     if (lane == 0) {
-      for (int it = 0; it < nsteps; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1;
-        mbar_wait(&bars[SB_EMPTY + s], ph ^ 1);
+      auto load_w = [&](int it, int s) {
         uint8_t* st = smem + s * STAGE;
         mbar_expect_tx(&bars[SB_FULL + s], STAGE);
-        if (it < n1) {
-          tma_load_2d(st, &mapW1, &bars[SB_FULL + s], (kb + it) * SK_BK, n0);
-          tma_load_2d(st + SK_W_BYTES, &mapX1, &bars[SB_FULL + s], (kb + it) * SK_BK, 0);
-        } else {
-          tma_load_2d(st, &mapW2, &bars[SB_FULL + s], (it - n1) * SK_BK, n0);
-          tma_load_2d(st + SK_W_BYTES, &mapX2, &bars[SB_FULL + s], (it - n1) * SK_BK, 0);
-        }
+        if (it < n1) tma_load_2d(st, &mapW1, &bars[SB_FULL + s], (kb + it) * SK_BK, n0);
+        else tma_load_2d(st, &mapW2, &bars[SB_FULL + s], (it - n1) * SK_BK, n0);
+      };
+      auto load_x = [&](int it, int s) {
+        uint8_t* st = smem + s * STAGE + SK_W_BYTES;
+        if (it < n1) tma_load_2d(st, &mapX1, &bars[SB_FULL + s], (kb + it) * SK_BK, 0);
+        else tma_load_2d(st, &mapX2, &bars[SB_FULL + s], (it - n1) * SK_BK, 0);
+      };
+      // PDL (common.cuh): the weights are constants - the first ring of W tiles is requested while the kernel that produces
+      // X (add + norm before in_proj, the layer core before out_proj) may still be running; X is only read after pdl_wait()
+      const int first = min(nsteps, kStages);
+      for (int it = 0; it < first; ++it) load_w(it, it);
+      pdl_wait();
+      for (int it = 0; it < first; ++it) load_x(it, it);
+      for (int it = first; it < nsteps; ++it) {
+        const int s = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(&bars[SB_EMPTY + s], ph ^ 1);
+        load_w(it, s);
+        load_x(it, s);
       }
     }
   } else if (warp == 1) {
@@ -197,6 +208,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_const
   }
   tc_fence_before();
   if (a.ksplit > 1) sk_cluster_sync(); else __syncthreads();
+  pdl_wait();   // (C is written below: nothing of the previous kernel may still be reading the buffer it occupies)
   if (warp >= 2) {
     // reduce 1 / ksplit of the batch rows over the cluster's partial tiles -> C[m][n0 ..]
     const int t = tid - 64;
@@ -261,17 +273,9 @@ int gemm_skinny(const omni_gemm_params_t* p, cudaStream_t s) {
     cudaFuncSetAttribute(gemm_skinny_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM);
     cudaFuncSetAttribute(gemm_skinny_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM);
   });
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(tiles_n * ksplit), 1, 1);
-  cfg.blockDim = dim3(SK_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = SK_SMEM;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)ksplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = MT == 64 ? cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<64, 8>, mW1, mX1, mW2, mX2, a)
-                           : cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<128, 6>, mW1, mX1, mW2, mX2, a);
+  const dim3 grid((unsigned)(tiles_n * ksplit)), block(SK_THREADS);
+  cudaError_t e = MT == 64 ? launch_pdl(kPdlGemm, gemm_skinny_kernel<64, 8>, grid, block, SK_SMEM, s, (unsigned)ksplit, mW1, mX1, mW2, mX2, a)
+                           : launch_pdl(kPdlGemm, gemm_skinny_kernel<128, 6>, grid, block, SK_SMEM, s, (unsigned)ksplit, mW1, mX1, mW2, mX2, a);
   if (e != cudaSuccess) return set_error(OMNI_CUDA_ERROR, "gemm_skinny_kernel launch: %s", cudaGetErrorString(e));
   count_launch();
   return OMNI_OK;

@@ -1,5 +1,6 @@
 // Library-level entry points: version, thread-local error message, launch counter.
 #include <atomic>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -28,6 +29,14 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled(int kind) {
+  static const int mask = [] {
+    const char* e = getenv("OMNI_PDL");
+    return e != nullptr ? atoi(e) : kPdlDefault;
+  }();
+  return (mask & kind) != 0;
 }
 
 }  // namespace omni

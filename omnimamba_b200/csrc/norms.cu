@@ -468,8 +468,10 @@ __global__ void __launch_bounds__(512) add_rms_fast_kernel(AddNormArgs a) {
   __shared__ float red[2][16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int col = tid * 8;
+  pdl_trigger();   // (PDL, common.cuh: the next kernel of the decode chain may start its prologue)
   float w[8];
   ld8<true>(a.w, a.w_dtype, col, 8, w);
+  pdl_wait();      // x / residual come from the previous kernel
   const T* xb = static_cast<const T*>(a.x.p);
   const float* rb = static_cast<const float*>(a.res.p);
   uint4 rx;
@@ -776,8 +778,8 @@ extern "C" int omni_add_norm_fwd(const omni_add_norm_fwd_params_t* p, void* stre
       (!present(p->residual_out) || p->residual_out.dtype == OMNI_F32)) {
     const unsigned threads = (unsigned)(D / 8);
     const unsigned gridp = (unsigned)std::min<int64_t>(M, (int64_t)sm_count() * (2048 / threads));
-    if (p->x.dtype == OMNI_BF16) add_rms_fast_kernel<__nv_bfloat16><<<gridp, threads, 0, s>>>(a);
-    else add_rms_fast_kernel<__half><<<gridp, threads, 0, s>>>(a);
+    if (p->x.dtype == OMNI_BF16) launch_pdl(kPdlAddNorm, add_rms_fast_kernel<__nv_bfloat16>, dim3(gridp), dim3(threads), 0, s, 1, a);
+    else launch_pdl(kPdlAddNorm, add_rms_fast_kernel<__half>, dim3(gridp), dim3(threads), 0, s, 1, a);
     OMNI_CUDA_LAUNCH_CHECK("add_rms_fast_kernel");
     return OMNI_OK;
   }
