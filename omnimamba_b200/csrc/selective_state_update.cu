@@ -163,10 +163,18 @@ template <typename TS> struct RawRow;   // one lane's 4 state elements of a row,
 template <> struct RawRow<float> { using type = float4; };
 template <> struct RawRow<__nv_bfloat16> { using type = uint2; };
 template <> struct RawRow<__half> { using type = uint2; };
-template <typename TS> constexpr int tied_rows() { return sizeof(TS) == 4 ? 16 : 32; }  // 8 KB of state per warp in flight
+#ifndef OMNI_SSU_ROWS16
+#define OMNI_SSU_ROWS16 16   // state rows per warp for a 16-bit state (fp32: half of it)
+#endif
+#ifndef OMNI_SSU_OCC
+#define OMNI_SSU_OCC 6       // CTAs (of kWarps warps) per SM the register budget is cut for
+#endif
+// (small tasks at a small register budget: many resident warps, each with 2 KB of state in flight, hide the latency of the
+// per-row scalars and the butterfly better than few warps with 8 KB each - the same finding as in decode_core.cu)
+template <typename TS> constexpr int tied_rows() { return sizeof(TS) == 4 ? OMNI_SSU_ROWS16 / 2 : OMNI_SSU_ROWS16; }
 
 template <typename TS>
-__global__ void __launch_bounds__(32 * kWarps) ssu_tied_kernel(SsuArgs a) {
+__global__ void __launch_bounds__(32 * kWarps, OMNI_SSU_OCC) ssu_tied_kernel(SsuArgs a) {
   constexpr int R = tied_rows<TS>();
   using Raw = typename RawRow<TS>::type;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -228,14 +236,13 @@ __global__ void __launch_bounds__(32 * kWarps) ssu_tied_kernel(SsuArgs a) {
       }
     }
   }
+  // (R < 32: the butterfly stops with 32 / R lanes holding partial sums of the same row)
   float y = acc[0];
-  int row = lane;
-  if constexpr (R == 16) {
-    y += __shfl_xor_sync(0xffffffffu, y, 1);
-    row = lane >> 1;
-  }
+#pragma unroll
+  for (int off = 1; off < 32 / R; off <<= 1) y += __shfl_xor_sync(0xffffffffu, y, off);
+  const int row = lane / (32 / R);
   const float x_r = __shfl_sync(0xffffffffu, xv, row);  // (the scalars of `row` live in lane `row`)
-  if (R == 32 || (lane & 1) == 0) {
+  if (lane % (32 / R) == 0) {
     const int pr = p0 + row;
     if (a.D) y = fmaf(x_r, ld_any(a.D, a.D_dtype, h * a.D_h + pr * a.D_p), y);
     if (a.z) y *= silu_f(ld_any(a.z, a.x_dtype, b * a.z_b + h * a.z_h + pr * a.z_p));

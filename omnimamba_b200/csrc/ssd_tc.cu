@@ -869,12 +869,19 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           }
           tmem_ld_wait();
           const float eh = hx == 0 ? eL0 : eL1;
-          // (scalar FFMA: the packed FFMA2 form spent ~3 register moves per instruction on operand pairing here)
+          // (scalar FFMA or the packed FFMA2 form, -DOMNI_EPI_FFMA2: measured equal, 377.7 vs 376.2 us, although the packed form
+          // executes ~900 more instructions per chunk on operand pairing - the kernel is not issue-bound)
           float2 y[16];
+#ifdef OMNI_EPI_FFMA2
+          const float2 ee = make_float2(eh, eh);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) y[e] = fma2(u2f2(v0[2 * e], v0[2 * e + 1]), ee, u2f2(v1[2 * e], v1[2 * e + 1]));
+#else
 #pragma unroll
           for (int e = 0; e < 16; ++e)
             y[e] = make_float2(fmaf(__uint_as_float(v0[2 * e]), eh, __uint_as_float(v1[2 * e])),
                                fmaf(__uint_as_float(v0[2 * e + 1]), eh, __uint_as_float(v1[2 * e + 1])));
+#endif
           if (half == 1) {  // both accumulators of this head have been read
             tc_fence_before();
             __syncwarp();

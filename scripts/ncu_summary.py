@@ -48,7 +48,8 @@ def main():
     src = ncu_csv(rep, "source")
     h2 = src[1]
     idx = {h: i for i, h in enumerate(h2)}
-    data = [r for r in src[2:] if len(r) == len(h2)]
+    # (a report with several launches repeats the two header rows per kernel: keep the instruction rows only)
+    data = [r for r in src[2:] if len(r) == len(h2) and r[idx["# Samples"]].isdigit()]
     st = collections.Counter()
     for r in data:
         for h in h2:
