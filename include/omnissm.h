@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OMNI_ABI_VERSION 5
+#define OMNI_ABI_VERSION 6
 #if defined(__GNUC__)
 #define OMNI_API __attribute__((visibility("default")))
 #else
@@ -269,8 +269,15 @@ typedef struct omni_gemm_params {
 } omni_gemm_params_t;
 OMNI_API int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream);
 OMNI_API int omni_gemm_bf16_supported(void); /* 1 if the driver exports cuTensorMapEncodeTiled */
-/* debug: tile scheme of omni_gemm_bf16 - 0 automatic, 1 single-CTA 128 x 256 tiles only, 2 CTA pairs (256 x 256) whenever legal */
+/* debug: tile scheme of omni_gemm_bf16 - 0 automatic, 1 single-CTA 128 x 256 tiles only, 2 CTA pairs (256 x 256) whenever legal,
+ * 3 automatic without the weight-streaming kernel for decode shapes (M <= 128; csrc/gemm_skinny.cu); 10 + k (k = 0, 1, 2, 4):
+ * K split of that kernel forced to k CTAs per cluster (0 = automatic again) */
 OMNI_API void omni_debug_set_gemm_mode(int mode);
+/* debug: which kernels of the decode chain [Mamba2.step behind /root/reference/models/stage2/generation.py:383-431: add + norm
+ * -> in_proj -> layer core -> out_proj per layer] may start before their predecessor in the stream has finished
+ * (programmatic dependent launch): bit 0 add + norm, bit 1 the weight-streaming GEMM, bit 2 the layer core; 0 = every launch
+ * fully serialised.  Default 3 (or OMNI_PDL from the environment).  Results are bit-identical for every mask. */
+OMNI_API void omni_debug_set_pdl(int mask);
 
 /* ---- fused training forward (path A) --------------------------------------------------------- */
 /* mamba_split_conv1d_scan_combined forward [mamba_ssm/ops/triton/ssd_combined.py: MambaSplitConv1dScanCombinedFn.forward;

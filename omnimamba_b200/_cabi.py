@@ -139,7 +139,7 @@ ENTRY_POINTS = {
     "omni_softmax_ce_bwd": SoftmaxCe,
 }
 OTHER_SYMBOLS = ["omni_version", "omni_last_error", "omni_launch_count", "omni_reset_launch_count",
-                 "omni_ssd_bwd_workspace_elems", "omni_selective_scan_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint", "omni_debug_set_bwd_trace", "omni_debug_set_handoff", "omni_gemm_bf16_supported", "omni_debug_set_gemm_mode", "omni_ssd_bwd_tc_supported", "omni_ssd_fwd_tc_supported"]
+                 "omni_ssd_bwd_workspace_elems", "omni_selective_scan_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint", "omni_debug_set_bwd_trace", "omni_debug_set_handoff", "omni_gemm_bf16_supported", "omni_debug_set_gemm_mode", "omni_debug_set_pdl", "omni_ssd_bwd_tc_supported", "omni_ssd_fwd_tc_supported"]
 
 # OMNI_LIB_PATH: A/B experiments only (a second build of the same library, e.g. scripts/ab_build.sh); the product path is
 # the in-tree lib/libomnissm.so
@@ -186,6 +186,8 @@ def lib() -> C.CDLL:
     l.omni_ssd_fwd_tc_supported.restype = C.c_int
     l.omni_debug_set_gemm_mode.argtypes = [C.c_int]
     l.omni_debug_set_gemm_mode.restype = None
+    l.omni_debug_set_pdl.argtypes = [C.c_int]
+    l.omni_debug_set_pdl.restype = None
     l.omni_debug_set_handoff.argtypes = [C.c_uint, C.c_int]
     l.omni_debug_set_handoff.restype = None
     _lib = l

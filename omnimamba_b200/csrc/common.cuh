@@ -54,6 +54,7 @@ int sm_count();  // of the current device (cached per device)
 // OMNI_PDL in the environment is a mask of the kernels that may start early (kPdl*); 0 launches everything fully serialised.
 enum { kPdlAddNorm = 1, kPdlGemm = 2, kPdlCore = 4, kPdlDefault = 3 };
 bool pdl_enabled(int kind);
+void set_pdl_mask(int mask);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                               unsigned cluster_x, Args... args) {

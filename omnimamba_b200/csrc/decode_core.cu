@@ -13,6 +13,8 @@
 // writes their shifted state back only after a cluster barrier.  HBM traffic = the state (read + write) + O(d_in_proj).
 #include <cooperative_groups.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -20,7 +22,11 @@ namespace cg = cooperative_groups;
 namespace omni {
 namespace {
 
-constexpr int kP = 64, kN = 128, kHeadsPerCta = 8, kCluster = 8, kDecThreads = 256;
+#ifndef OMNI_DEC_HEADS
+#define OMNI_DEC_HEADS 8   // heads (= warps) per CTA; 64 / OMNI_DEC_HEADS CTAs form the cluster of a sequence (4 -> 16, non-portable size)
+#endif
+constexpr int kP = 64, kN = 128, kHeadsPerCta = OMNI_DEC_HEADS, kCluster = 64 / OMNI_DEC_HEADS, kDecThreads = 32 * OMNI_DEC_HEADS;
+constexpr int kBcPerThread = 2 * kN / kDecThreads;   // B / C conv channels per thread (every CTA computes all 256)
 constexpr int kMaxW = 4;
 
 struct DecArgs {
@@ -96,12 +102,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads, 
   // ---- 1. conv-state update + SiLU: 2 x channels per thread (this CTA's heads) + 1 B/C channel per thread (all CTAs) ----
   const char* zrow = static_cast<const char*>(a.zx);
   auto zx_at = [&](int col) { return ld_any(a.zx, a.io_dtype, (int64_t)b * a.zx_b + col); };
-  float bc_keep[kMaxW];  // the shifted B / C state of this thread's channel (written back by rank 0 after the barrier)
+  float bc_keep[kBcPerThread][kMaxW];  // the shifted B / C state of this thread's channels (written back by rank 0 after the barrier)
   (void)zrow;
 #pragma unroll
-  for (int which = 0; which < 3; ++which) {
-    // which 0, 1: x channels (cr * 512 + tid * 2 + which);  2: B / C channel dim + tid
-    const int ch = which < 2 ? cr * (kHeadsPerCta * kP) + tid * 2 + which : dim + tid;
+  for (int which = 0; which < 2 + kBcPerThread; ++which) {
+    // which 0, 1: x channels (cr * 2 T + tid * 2 + which);  2 ..: B / C channels dim + tid + T (which - 2)
+    const int bci = tid + kDecThreads * (which - 2);
+    const int ch = which < 2 ? cr * (kHeadsPerCta * kP) + tid * 2 + which : dim + bci;
     float st[kMaxW];
 #pragma unroll
     for (int k = 0; k < kMaxW; ++k)
@@ -118,18 +125,21 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads, 
       for (int k = 0; k < kMaxW; ++k)
         if (k < a.W) st_any(a.conv_state, a.cs_dtype, (int64_t)b * a.cs_b + (int64_t)ch * a.cs_c + (int64_t)k * a.cs_k, st[k]);
     } else {
-      if (tid < kN) Bs[tid] = u; else Cs[tid - kN] = u;
+      if (bci < kN) Bs[bci] = u; else Cs[bci - kN] = u;
 #pragma unroll
-      for (int k = 0; k < kMaxW; ++k) bc_keep[k] = st[k];
+      for (int k = 0; k < kMaxW; ++k) bc_keep[which - 2][k] = st[k];
     }
   }
   __syncthreads();
   cluster.sync();   // every CTA of the sequence has read the old B / C conv state
   if (cr == 0) {
-    const int ch = dim + tid;
 #pragma unroll
-    for (int k = 0; k < kMaxW; ++k)
-      if (k < a.W) st_any(a.conv_state, a.cs_dtype, (int64_t)b * a.cs_b + (int64_t)ch * a.cs_c + (int64_t)k * a.cs_k, bc_keep[k]);
+    for (int j = 0; j < kBcPerThread; ++j) {
+      const int ch = dim + tid + kDecThreads * j;
+#pragma unroll
+      for (int k = 0; k < kMaxW; ++k)
+        if (k < a.W) st_any(a.conv_state, a.cs_dtype, (int64_t)b * a.cs_b + (int64_t)ch * a.cs_c + (int64_t)k * a.cs_k, bc_keep[j][k]);
+    }
   }
 
   // ---- 2. selective state update: warp = head, R rows per step, lane = 4 consecutive n ----------------------------------
@@ -253,6 +263,14 @@ extern "C" int omni_mamba2_decode_core(const omni_mamba2_decode_core_params_t* p
   a.D_dtype = p->D.dtype; a.db_dtype = p->dt_bias.dtype; a.nw_dtype = p->norm_weight.dtype;
   a.eps = p->eps;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (kCluster > 8) {  // 16-CTA clusters are a non-portable size: opt in once
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(mamba2_decode_core_kernel<float>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(mamba2_decode_core_kernel<__nv_bfloat16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(mamba2_decode_core_kernel<__half>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    });
+  }
   const unsigned grid = (unsigned)(Bsz * kCluster);
   switch (st.dtype) {   // (cluster dims are compile-time: __cluster_dims__)
     case OMNI_F32: launch_pdl(kPdlCore, mamba2_decode_core_kernel<float>, dim3(grid), dim3(kDecThreads), 0, s, 1, a); break;

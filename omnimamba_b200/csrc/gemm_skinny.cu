@@ -130,6 +130,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_const
     tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapX1);
     if (a.K2 > 0) { tma_prefetch_desc(&mapW2); tma_prefetch_desc(&mapX2); }
   }
+  __syncwarp();   // (warp 0 ran the single-thread set-up above: converge before the aligned barrier)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -163,6 +164,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_const
         load_x(it, s);
       }
     }
+    __syncwarp();   // (the cluster barrier below is .aligned: the warp must arrive converged)
   } else if (warp == 1) {
     // ============ MMA issuer: D[n 128][m MT] += W[n][k] X[m][k] =========================================================
     const bool leader = sk_elect();
@@ -252,7 +254,8 @@ int gemm_skinny(const omni_gemm_params_t* p, cudaStream_t s) {
   int ksplit = 1;
   for (int c = 2; c <= 4; c *= 2)
     if ((int64_t)tiles_n * c <= sm_count() && nk1 / c >= 4) ksplit = c;
-  if (g_skinny_ksplit > 0) ksplit = g_skinny_ksplit;   // debug override (omni_debug_set_gemm_mode(10 + ksplit))
+  // debug override (omni_debug_set_gemm_mode(10 + ksplit)), honoured while the grid stays one wave
+  if (g_skinny_ksplit > 0 && (int64_t)tiles_n * g_skinny_ksplit <= sm_count()) ksplit = g_skinny_ksplit;
   SkinnyArgs a{};
   a.M = (int)M; a.N = (int)N; a.K1 = (int)K1; a.K2 = (int)K2;
   a.ksplit = ksplit; a.ksteps1 = (nk1 + ksplit - 1) / ksplit;

@@ -31,13 +31,17 @@ int sm_count() {
   return cached[dev];
 }
 
+static std::atomic<int> g_pdl_mask{-1};  // -1: not read from the environment yet
 bool pdl_enabled(int kind) {
-  static const int mask = [] {
+  int m = g_pdl_mask.load(std::memory_order_relaxed);
+  if (m < 0) {
     const char* e = getenv("OMNI_PDL");
-    return e != nullptr ? atoi(e) : kPdlDefault;
-  }();
-  return (mask & kind) != 0;
+    m = e != nullptr ? atoi(e) & 7 : kPdlDefault;
+    g_pdl_mask.store(m, std::memory_order_relaxed);
+  }
+  return (m & kind) != 0;
 }
+void set_pdl_mask(int mask) { g_pdl_mask.store(mask & 7, std::memory_order_relaxed); }
 
 }  // namespace omni
 
@@ -46,4 +50,7 @@ int omni_version(void) { return OMNI_ABI_VERSION; }
 const char* omni_last_error(void) { return omni::g_err; }
 int64_t omni_launch_count(void) { return omni::g_launches.load(std::memory_order_relaxed); }
 void omni_reset_launch_count(void) { omni::g_launches.store(0, std::memory_order_relaxed); }
+/* debug: which kernels of the decode chain may start early (programmatic dependent launch): 1 add + norm, 2 weight-streaming
+ * GEMM, 4 layer core; 0 = every launch fully serialised.  Default 3, or OMNI_PDL from the environment. */
+void omni_debug_set_pdl(int mask) { omni::set_pdl_mask(mask); }
 }

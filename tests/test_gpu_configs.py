@@ -330,3 +330,63 @@ def test_decode_core_matches_oracle_and_unfused_step(dtype):
         graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(y_graph, y_eager) and torch.equal(conv, c1) and torch.equal(ssm, s1)
+
+
+@pytest.mark.parametrize("lora", [False, True])
+def test_decode_chain_is_bit_identical_under_programmatic_dependent_launch(lora):
+    """The decode step of BASELINE config 4 (add + norm -> in_proj -> layer core -> out_proj per layer, batch 64, d_model 2048,
+    bf16, captured in a CUDA graph as models/stage2/generation.py:383-431 does) launches its kernels with programmatic
+    dependent launch: the weight-streaming GEMM and add + norm may start - and prefetch weights - while their predecessor
+    still runs.  Outputs and both caches after three replayed tokens must be BIT-identical for every mask of kernels allowed
+    to start early (0 = fully serialised; 3 = default; 7 = all), and the GEMMs must be the weight-streaming kernel."""
+    from omnimamba_b200 import _cabi
+    from omnimamba_b200.backbone import InferenceParams, MixerStack
+    torch.manual_seed(5)
+    n_layer, B, L0 = 4, 64, 16
+    stack = MixerStack(2048, n_layer, device=DEV, dtype=torch.bfloat16, lora=lora).eval()
+    if lora:
+        stack.set_lora_mode("t2i")
+        for name, p in stack.named_parameters():   # (B adapters start at zero: give the LoRA pair something to add)
+            if "lora_B" in name:
+                torch.nn.init.normal_(p, std=0.02)
+    ip = InferenceParams(max_seqlen=64, max_batch_size=B)
+    lib = _cabi.lib()
+    results = {}
+    with torch.no_grad():
+        stack(torch.randn(B, L0, 2048, device=DEV, dtype=torch.bfloat16), ip)
+        ip.seqlen_offset = L0
+        caches0 = {k: (c.clone(), s.clone()) for k, (c, s) in ip.key_value_memory_dict.items()}
+        tok = torch.randn(B, 1, 2048, device=DEV, dtype=torch.bfloat16)
+        for mask in (0, 3, 7):
+            try:
+                lib.omni_debug_set_pdl(mask)
+                for k, (c, s) in ip.key_value_memory_dict.items():
+                    c.copy_(caches0[k][0]); s.copy_(caches0[k][1])
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    stack(tok, ip)
+                torch.cuda.current_stream().wait_stream(side)
+                for k, (c, s) in ip.key_value_memory_dict.items():
+                    c.copy_(caches0[k][0]); s.copy_(caches0[k][1])
+                graph = torch.cuda.CUDAGraph()
+                _cabi.reset_launch_count()
+                with torch.cuda.graph(graph):
+                    out = stack(tok, ip)
+                launches = _cabi.launch_count()
+                for k, (c, s) in ip.key_value_memory_dict.items():
+                    c.copy_(caches0[k][0]); s.copy_(caches0[k][1])
+                for _ in range(3):
+                    graph.replay()
+                torch.cuda.synchronize()
+                results[mask] = (out.clone(), {k: (c.clone(), s.clone()) for k, (c, s) in ip.key_value_memory_dict.items()}, launches)
+            finally:
+                lib.omni_debug_set_pdl(3)
+    o0, c0, n0 = results[0]
+    assert torch.isfinite(o0.float()).all() and n0 >= 4 * n_layer
+    for mask in (3, 7):
+        o, c, n = results[mask]
+        assert n == n0
+        assert torch.equal(o, o0), f"PDL mask {mask}: output differs from the serialised launch"
+        for k in c0:
+            assert torch.equal(c[k][0], c0[k][0]) and torch.equal(c[k][1], c0[k][1]), f"PDL mask {mask}: caches of layer {k} differ"
