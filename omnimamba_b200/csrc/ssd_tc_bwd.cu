@@ -237,6 +237,27 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     return __half2float(__ushort_as_half((unsigned short)bits));
   };
   uint32_t dt_next = load_dt(item_lo);
+  // The six tiles of an item (TMA thread only).  They are requested as soon as the PREVIOUS item's last MMA group has read its
+  // tiles (BB_C8) - ~1000 cycles before the item starts - unless that item ends a (batch, chunk) group, whose dC / dB flush
+  // stages through the x and B tiles.
+  auto issue_loads = [&](int item_) {
+    const int hp_ = item_ % HP, bc_ = item_ / HP, c_ = bc_ % a.nchunks, b_ = bc_ / a.nchunks;
+    const int h0_ = hp_ * 2, grp_ = h0_ / hpg, t0_ = c_ * Q;
+    mbar_expect_tx(&bars[BB_TMA], 6 * 32768);
+    tma_load_4d(smem + SM_X, &mapX, &bars[BB_TMA], 0, h0_, t0_, b_);
+    tma_load_4d(smem + SM_X + 16384, &mapX, &bars[BB_TMA], 0, h0_ + 1, t0_, b_);
+    tma_load_4d(smem + SM_DY, &mapDY, &bars[BB_TMA], 0, h0_, t0_, b_);
+    tma_load_4d(smem + SM_DY + 16384, &mapDY, &bars[BB_TMA], 0, h0_ + 1, t0_, b_);
+    tma_load_4d(smem + SM_B, &mapB, &bars[BB_TMA], 0, grp_, t0_, b_);
+    tma_load_4d(smem + SM_B + 16384, &mapB, &bars[BB_TMA], 64, grp_, t0_, b_);
+    tma_load_4d(smem + SM_C, &mapC, &bars[BB_TMA], 0, grp_, t0_, b_);
+    tma_load_4d(smem + SM_C + 16384, &mapC, &bars[BB_TMA], 64, grp_, t0_, b_);
+    tma_load_4d(smem + SM_S, &mapS, &bars[BB_TMA], 0, h0_ * HD, c_, b_);
+    tma_load_4d(smem + SM_S + 16384, &mapS, &bars[BB_TMA], 64, h0_ * HD, c_, b_);
+    tma_load_4d(smem + SM_DS, &mapDS, &bars[BB_TMA], 0, h0_ * HD, c_, b_);
+    tma_load_4d(smem + SM_DS + 16384, &mapDS, &bars[BB_TMA], 64, h0_ * HD, c_, b_);
+  };
+  bool loads_issued = false;   // (meaningful in the TMA thread only)
 #pragma unroll 1
   for (int item = item_lo; item < item_hi; ++item, ph ^= 1, ++it_count) {
     const int hp = item % HP, bc = item / HP, c = bc % a.nchunks, b = bc / a.nchunks;
@@ -244,22 +265,10 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const bool last_of_group = item + 1 == item_hi || (item + 1) / HP != bc || (h0 + 2) / hpg != grp;
 
     BTR(0);
-    // ---- A. tile loads (one thread) and the decay tables (threads 0..255: head tid >> 7, token tid & 127) -----------
-    if (tid == kTmaThread) {
-      mbar_expect_tx(&bars[BB_TMA], 6 * 32768);
-      tma_load_4d(smem + SM_X, &mapX, &bars[BB_TMA], 0, h0, t0, b);
-      tma_load_4d(smem + SM_X + 16384, &mapX, &bars[BB_TMA], 0, h0 + 1, t0, b);
-      tma_load_4d(smem + SM_DY, &mapDY, &bars[BB_TMA], 0, h0, t0, b);
-      tma_load_4d(smem + SM_DY + 16384, &mapDY, &bars[BB_TMA], 0, h0 + 1, t0, b);
-      tma_load_4d(smem + SM_B, &mapB, &bars[BB_TMA], 0, grp, t0, b);
-      tma_load_4d(smem + SM_B + 16384, &mapB, &bars[BB_TMA], 64, grp, t0, b);
-      tma_load_4d(smem + SM_C, &mapC, &bars[BB_TMA], 0, grp, t0, b);
-      tma_load_4d(smem + SM_C + 16384, &mapC, &bars[BB_TMA], 64, grp, t0, b);
-      tma_load_4d(smem + SM_S, &mapS, &bars[BB_TMA], 0, h0 * HD, c, b);
-      tma_load_4d(smem + SM_S + 16384, &mapS, &bars[BB_TMA], 64, h0 * HD, c, b);
-      tma_load_4d(smem + SM_DS, &mapDS, &bars[BB_TMA], 0, h0 * HD, c, b);
-      tma_load_4d(smem + SM_DS + 16384, &mapDS, &bars[BB_TMA], 64, h0 * HD, c, b);
-    }
+    // ---- A. tile loads (one thread; normally already issued at the end of the previous item, see `issue_loads`) and the
+    //         decay tables (threads 0..255: head tid >> 7, token tid & 127) ---------------------------------------------
+    if (tid == kTmaThread && !loads_issued) issue_loads(item);
+    loads_issued = false;
     float my_dt = 0.f, my_lam = 0.f;
     const int th = (tid >> 7) & 1, tj = tid & 127;  // (head, token) of the table threads
     if (tid < 256) {
@@ -688,6 +697,11 @@ ssd_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     fresh = false;
     mbar_wait(&bars[BB_C8], ph);   // G6 / G8 have read the S / dS / x / dy tiles (next item's loads) and completed dC / dB (flush)
     tc_fence_after();
+    if (tid == kTmaThread && !last_of_group && item + 1 < item_hi) {
+      // every MMA group of this item is complete and no SIMT phase below reads a tile: the next item's loads start now
+      issue_loads(item + 1);
+      loads_issued = true;
+    }
     // ---- N2. end of a (batch, chunk) group: dC (R2), dB (R3): TMEM -> fp32 staging over the dead x/dy and B/C tiles ->
     //          coalesced vector reductions ----------------------------------------------------------------------------------
     if (last_of_group) {
