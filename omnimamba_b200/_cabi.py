@@ -195,35 +195,53 @@ def lib() -> C.CDLL:
 
 
 def tdesc(t: Optional[torch.Tensor]) -> Tensor:
-    """Describe a CUDA tensor (or None -> absent) for the C ABI."""
+    """Describe a CUDA tensor (or None -> absent) for the C ABI.  (Hot on the host side: at the 72-token prefill of
+    inference_t2i.py the kernels take 3-16 us and this wrapper layer used to take 35-70 us per call - scripts/
+    bench_host_overhead.py - so shapes and strides are assigned as slices and nothing is looked up twice.)"""
     d = Tensor()
     if t is None:
         return d
     if not t.is_cuda:
         raise RuntimeError("omnimamba_b200 kernels need CUDA tensors (no CPU fallback); got a tensor on " + str(t.device))
-    if t.dtype not in _DTYPES:
+    dt = _DTYPES.get(t.dtype)
+    if dt is None:
         raise TypeError(f"unsupported dtype {t.dtype}")
-    if t.dim() > OMNI_MAX_DIMS:
+    n = t.dim()
+    if n > OMNI_MAX_DIMS:
         raise ValueError("too many dimensions")
-    d.data = t.data_ptr() if t.numel() > 0 else 0
-    if t.numel() == 0:
-        # keep "present" semantics for empty tensors: give them a non-null dummy address
-        d.data = 1 << 4
-    d.dtype = _DTYPES[t.dtype]
-    d.ndim = t.dim()
-    for i in range(t.dim()):
-        d.shape[i] = t.shape[i]
-        d.stride[i] = t.stride(i)
+    # keep "present" semantics for empty tensors: give them a non-null dummy address
+    d.data = t.data_ptr() if t.numel() > 0 else 1 << 4
+    d.dtype = dt
+    d.ndim = n
+    if n:
+        d.shape[0:n] = t.shape
+        d.stride[0:n] = t.stride()
     return d
+
+
+_FN_CACHE = {}
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream   # (the accessor Triton's launcher uses: no Stream object is built)
+except AttributeError:  # pragma: no cover
+    _raw_stream = None
 
 
 def call(name: str, params: C.Structure, device: torch.device) -> None:
     """Invoke an entry point on the current stream of `device`; raise on a non-zero status."""
-    l = lib()
-    with torch.cuda.device(device):
-        stream = torch.cuda.current_stream(device).cuda_stream
-        rc = getattr(l, name)(C.byref(params), C.c_void_p(stream))
+    fn = _FN_CACHE.get(name)
+    if fn is None:
+        fn = _FN_CACHE[name] = getattr(lib(), name)
+    idx = device.index
+    cur = torch.cuda.current_device()
+    if (idx is None or idx == cur) and _raw_stream is not None:
+        # (the usual case - the tensors live on the current device: no device-guard context manager, ~10 us of Python)
+        rc = fn(C.byref(params), C.c_void_p(_raw_stream(cur)))
+    else:
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            rc = fn(C.byref(params), C.c_void_p(stream))
     if rc != 0:
+        l = lib()
         msg = l.omni_last_error().decode("utf-8", "replace")
         kind = _STATUS.get(rc, str(rc))
         if rc in (1, 2, 3):
