@@ -239,7 +239,8 @@ int skinny_map(CUtensorMap* m, const omni_tensor_t& t, int rows_box) {  // K-maj
 
 // Does the decode-shaped path take this GEMM?  (K-major operands, M <= 128, enough weight rows to be worth a stream.)
 bool gemm_skinny_eligible(int64_t M, int64_t N, int64_t K1, int64_t K2, int amaj, int bmaj) {
-  return M >= 1 && M <= 128 && N >= 256 && K1 >= 256 && amaj == 0 && bmaj == 0 && K2 >= 0;
+  // (N % 8: the reduction writes groups of four consecutive n with one vector store)
+  return M >= 1 && M <= 128 && N >= 256 && N % 8 == 0 && K1 >= 256 && amaj == 0 && bmaj == 0 && K2 >= 0;
 }
 
 int gemm_skinny(const omni_gemm_params_t* p, cudaStream_t s) {
