@@ -15,7 +15,7 @@
 
 #include <mutex>
 
-#include "common.cuh"
+#include "umma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -76,9 +76,17 @@ template <> __device__ __forceinline__ uint2 pack4<__half>(const float (&o)[4]) 
 // at once (592 slots), there is no second wave, and the phases of one CTA hide behind the state streams of the three others.
 // Measured at batch 64, bf16 state (scripts/bench_decode_core.py, same box): 2 CTAs x 32-row steps 38.0 us, 3 x 16 47.0, 4 x 16
 // 41.2 (spills), 4 x 8 33.1, 4 x 4 33.6, 5 x 8 38.2 (spills), 5 x 4 34.4, 6 x 4 35.6;  fp32 state: 59.4 -> 55.7 us.
+#ifndef OMNI_DEC_BULK
+#define OMNI_DEC_BULK 0    // 1: the state rows arrive through bulk async copies into a per-warp ring in shared memory (no registers held
+#endif                     // by loads in flight); 0: plain vector loads into registers.  Measured: 34.7 vs 33.4 us (bf16), 57.7 vs 56.1
+                           // (fp32) - bytes in flight are not what limits the kernel, the 3-or-4-CTAs-per-SM granularity is
+constexpr int kDecRing = 3;                  // ring slots per warp
+constexpr int kDecSlotBytes = 2048;          // one step of R rows (8 x 256 B for a 16-bit state, 4 x 512 B for fp32)
+constexpr int kDecDynSmem = OMNI_DEC_BULK ? kDecThreads / 32 * kDecRing * kDecSlotBytes : 0;   // 48 KB per CTA: four CTAs per SM
 template <typename TS>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads, OMNI_DEC_OCC) mamba2_decode_core_kernel(DecArgs a) {
   constexpr int R = sizeof(TS) == 4 ? OMNI_DEC_ROWS16 / 2 : OMNI_DEC_ROWS16;   // state rows per warp step
+  static_assert(!OMNI_DEC_BULK || R * kN * (int)sizeof(TS) == kDecSlotBytes, "a ring slot holds one step");
   using Raw = typename Raw4<TS>::type;
   cg::cluster_group cluster = cg::this_cluster();
   const int cr = (int)cluster.block_rank();           // 8 heads of the sequence
@@ -94,9 +102,35 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads, 
   // while the conv phase and the first cluster barrier run)
   const int h_w = cr * kHeadsPerCta + warp;
   TS* const sbase = static_cast<TS*>(a.state) + (int64_t)b * a.st_b + (int64_t)h_w * a.st_h + lane * 4;
+#if OMNI_DEC_BULK
+  // State stream, bulk version: the 64 rows of this warp's head are contiguous (host-checked), 2 KB steps of R rows travel
+  // global -> shared memory as cp.async.bulk copies into a ring of kDecRing slots per warp, each completing on its own
+  // mbarrier.  Bytes in flight cost no registers: 4 CTAs x 8 warps x 3 slots x 2 KB = 192 KB per SM can be outstanding (the
+  // register version holds 64 KB), which is what the ~1.5 us HBM latency needs at this bandwidth.  The updated rows go back
+  // with ordinary vector stores, so a slot is free again as soon as the warp has read it.
+  extern __shared__ __align__(128) uint8_t dec_ring[];
+  __shared__ __align__(8) uint64_t ring_bar[kDecThreads / 32][kDecRing];
+  uint8_t* const my_ring = dec_ring + warp * (kDecRing * kDecSlotBytes);
+  const TS* const gslice = static_cast<const TS*>(a.state) + (int64_t)b * a.st_b + (int64_t)h_w * a.st_h;   // 64 x 128 contiguous
+  constexpr int kSteps = kP / R;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kDecRing; ++k) umma::mbar_init(&ring_bar[warp][k], 1);
+    umma::mbar_fence_init();
+#pragma unroll
+    for (int k = 0; k < kDecRing; ++k) {   // the state does not depend on the previous kernel: requested before pdl_wait()
+      umma::mbar_expect_tx(&ring_bar[warp][k], kDecSlotBytes);
+      umma::bulk_load_1d(my_ring + k * kDecSlotBytes, gslice + (int64_t)k * R * kN, kDecSlotBytes, &ring_bar[warp][k]);
+    }
+  }
+  __syncwarp();
+#else
+  // (measured and not kept: a different starting step per warp, against DRAM channel camping - 32.7 vs 33.2 us, noise)
+  constexpr int rot = 0;
   Raw raw[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) raw[r] = *reinterpret_cast<const Raw*>(sbase + (int64_t)r * a.st_p);
+  for (int r = 0; r < R; ++r) raw[r] = *reinterpret_cast<const Raw*>(sbase + (int64_t)(rot + r) * a.st_p);
+#endif
 
   pdl_wait();      // zxbcdt comes from the previous kernel (in_proj)
   // ---- 1. conv-state update + SiLU: 2 x channels per thread (this CTA's heads) + 1 B/C channel per thread (all CTAs) ----
@@ -153,11 +187,28 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kDecThreads, 
 #pragma unroll
     for (int e = 0; e < 4; ++e) { Bv[e] = Bs[n + e] * dtv; Cv[e] = Cs[n + e]; }   // (dt folded into B: S += x_p (dt B))
 #pragma unroll 1
-    for (int p0 = 0; p0 < kP; p0 += R) {
-      if (p0 > 0) {
+    for (int pstep = 0; pstep < kP; pstep += R) {
+#if OMNI_DEC_BULK
+      const int p0 = pstep;
+      const int step = p0 / R, slot = step % kDecRing;
+      while (!umma::mbar_try_wait(&ring_bar[warp][slot], (uint32_t)((step / kDecRing) & 1))) {
+      }
+      Raw raw[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        raw[r] = *reinterpret_cast<const Raw*>(my_ring + slot * kDecSlotBytes + (r * kN + lane * 4) * (int)sizeof(TS));
+      __syncwarp();   // every lane has read the slot: refill it with the step kDecRing ahead
+      if (lane == 0 && step + kDecRing < kSteps) {
+        umma::mbar_expect_tx(&ring_bar[warp][slot], kDecSlotBytes);
+        umma::bulk_load_1d(my_ring + slot * kDecSlotBytes, gslice + (int64_t)(step + kDecRing) * R * kN, kDecSlotBytes, &ring_bar[warp][slot]);
+      }
+#else
+      const int p0 = (pstep + rot) & (kP - 1);
+      if (pstep > 0) {
 #pragma unroll
         for (int r = 0; r < R; ++r) raw[r] = *reinterpret_cast<const Raw*>(sbase + (int64_t)(p0 + r) * a.st_p);
       }
+#endif
       float acc[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -232,6 +283,8 @@ extern "C" int omni_mamba2_decode_core(const omni_mamba2_decode_core_params_t* p
   OMNI_CHECK(present(st) && st.ndim == 4 && is_float_dtype(st.dtype) && st.shape[2] == kP && st.shape[3] == kN && st.stride[3] == 1 &&
                  st.stride[2] % 4 == 0 && st.stride[1] % 4 == 0 && st.stride[0] % 4 == 0 && aligned16(st.data),
              OMNI_UNSUPPORTED, "decode_core: ssm_state must be (B, H, 64, 128) with contiguous, 16-byte aligned rows");
+  OMNI_CHECK(!OMNI_DEC_BULK || st.stride[2] == kN, OMNI_UNSUPPORTED,
+             "decode_core: the (64, 128) state of a head must be contiguous (it is streamed with bulk copies)");
   const int64_t Bsz = st.shape[0], H = st.shape[1], dim = H * kP, conv_dim = dim + 2 * kN;
   OMNI_CHECK(H % kHeadsPerCta == 0 && H / kHeadsPerCta == kCluster, OMNI_UNSUPPORTED,
              "decode_core: built for nheads = 64 (d_model = 2048): one cluster of 8 CTAs x 8 heads per sequence");
@@ -263,6 +316,14 @@ extern "C" int omni_mamba2_decode_core(const omni_mamba2_decode_core_params_t* p
   a.D_dtype = p->D.dtype; a.db_dtype = p->dt_bias.dtype; a.nw_dtype = p->norm_weight.dtype;
   a.eps = p->eps;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (kDecDynSmem > 0) {  // static + dynamic shared memory exceed the 48 KB default: opt in once
+    static std::once_flag once_smem;
+    std::call_once(once_smem, [] {
+      cudaFuncSetAttribute(mamba2_decode_core_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecDynSmem);
+      cudaFuncSetAttribute(mamba2_decode_core_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecDynSmem);
+      cudaFuncSetAttribute(mamba2_decode_core_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecDynSmem);
+    });
+  }
   if (kCluster > 8) {  // 16-CTA clusters are a non-portable size: opt in once
     static std::once_flag once;
     std::call_once(once, [] {
@@ -273,9 +334,9 @@ extern "C" int omni_mamba2_decode_core(const omni_mamba2_decode_core_params_t* p
   }
   const unsigned grid = (unsigned)(Bsz * kCluster);
   switch (st.dtype) {   // (cluster dims are compile-time: __cluster_dims__)
-    case OMNI_F32: launch_pdl(kPdlCore, mamba2_decode_core_kernel<float>, dim3(grid), dim3(kDecThreads), 0, s, 1, a); break;
-    case OMNI_BF16: launch_pdl(kPdlCore, mamba2_decode_core_kernel<__nv_bfloat16>, dim3(grid), dim3(kDecThreads), 0, s, 1, a); break;
-    default: launch_pdl(kPdlCore, mamba2_decode_core_kernel<__half>, dim3(grid), dim3(kDecThreads), 0, s, 1, a); break;
+    case OMNI_F32: launch_pdl(kPdlCore, mamba2_decode_core_kernel<float>, dim3(grid), dim3(kDecThreads), kDecDynSmem, s, 1, a); break;
+    case OMNI_BF16: launch_pdl(kPdlCore, mamba2_decode_core_kernel<__nv_bfloat16>, dim3(grid), dim3(kDecThreads), kDecDynSmem, s, 1, a); break;
+    default: launch_pdl(kPdlCore, mamba2_decode_core_kernel<__half>, dim3(grid), dim3(kDecThreads), kDecDynSmem, s, 1, a); break;
   }
   OMNI_CUDA_LAUNCH_CHECK("mamba2_decode_core_kernel");
   return OMNI_OK;
