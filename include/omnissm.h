@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OMNI_ABI_VERSION 6
+#define OMNI_ABI_VERSION 7
 #if defined(__GNUC__)
 #define OMNI_API __attribute__((visibility("default")))
 #else
@@ -269,6 +269,13 @@ typedef struct omni_gemm_params {
 } omni_gemm_params_t;
 OMNI_API int omni_gemm_bf16(const omni_gemm_params_t* p, void* stream);
 OMNI_API int omni_gemm_bf16_supported(void); /* 1 if the driver exports cuTensorMapEncodeTiled */
+/* The same projection with fp32 operands and fp32 result, for decode shapes only (M = batch <= 128 rows, N >= 256, K >= 128,
+ * K-major a and b): what F.linear does on fp32 weights inside Mamba2.step when the model runs without autocast
+ * [/root/reference/scripts/inference_t2i.py:21-27 loads and runs the checkpoint in fp32;
+ * /root/reference/models/stage2/generation.py:383-431 is the decode loop].  The weights are streamed once and multiplied on
+ * the tensor cores with the error-compensated 3xTF32 split (hi / lo tiles, three MMAs per product): fp32-accurate
+ * (<= 2e-6 relative), HBM-bound instead of SGEMM-bound.  Other shapes: OMNI_UNSUPPORTED (the caller keeps its own GEMM). */
+OMNI_API int omni_gemm_f32_decode(const omni_gemm_params_t* p, void* stream);
 /* debug: tile scheme of omni_gemm_bf16 - 0 automatic, 1 single-CTA 128 x 256 tiles only, 2 CTA pairs (256 x 256) whenever legal,
  * 3 automatic without the weight-streaming kernel for decode shapes (M <= 128; csrc/gemm_skinny.cu); 10 + k (k = 0, 1, 2, 4):
  * K split of that kernel forced to k CTAs per cluster (0 = automatic again) */

@@ -133,6 +133,7 @@ ENTRY_POINTS = {
     "omni_selective_scan_fwd": SelScanFwd,
     "omni_selective_scan_bwd": SelScanBwd,
     "omni_gemm_bf16": Gemm,
+    "omni_gemm_f32_decode": Gemm,
     "omni_split_conv1d_scan_fwd": SplitConv1dScanFwd,
     "omni_mamba2_decode_core": DecodeCore,
     "omni_softmax_ce_fwd": SoftmaxCe,
@@ -305,4 +306,33 @@ def gemm(a, b, out_dtype=torch.bfloat16, a2=None, b2=None, out=None):
     p = Gemm()
     p.a, p.b, p.a2, p.b2, p.out = tdesc(a), tdesc(b), tdesc(a2), tdesc(b2), tdesc(out)
     call("omni_gemm_bf16", p, a.device)
+    return out
+
+
+def gemm_f32_decode_ok(a, b, a2=None, b2=None) -> bool:
+    """True when omni_gemm_f32_decode (3xTF32 weight-streaming kernel) takes these fp32 operands: decode shapes only."""
+    def row_major(t):
+        r, c = t.shape
+        return t.dim() == 2 and t.dtype == torch.float32 and t.data_ptr() % 16 == 0 and (c <= 1 or t.stride(1) == 1) and \
+            (r <= 1 or (t.stride(0) % 4 == 0 and t.stride(0) >= c))
+    if a.dim() != 2 or b.dim() != 2 or not (row_major(a) and row_major(b)) or a.shape[1] != b.shape[1]:
+        return False
+    M, K = a.shape
+    N = b.shape[0]
+    if not (1 <= M <= 128 and N >= 256 and N % 4 == 0 and K >= 128 and K % 4 == 0):
+        return False
+    if a2 is not None:
+        if not (row_major(a2) and row_major(b2)) or a2.shape[1] % 4 or a2.shape[0] != M or b2.shape[0] != N:
+            return False
+    return gemm_supported()
+
+
+def gemm_f32_decode(a, b, a2=None, b2=None, out=None):
+    """out (M, N) = a (M, K) @ b (N, K)^T [+ a2 @ b2^T], fp32 operands and result, on the 3xTF32 weight-streaming kernel."""
+    M, N = a.shape[0], b.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    p = Gemm()
+    p.a, p.b, p.a2, p.b2, p.out = tdesc(a), tdesc(b), tdesc(a2), tdesc(b2), tdesc(out)
+    call("omni_gemm_f32_decode", p, a.device)
     return out

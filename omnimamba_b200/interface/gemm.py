@@ -106,6 +106,20 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db, dx2, dw2
 
 
+def _f32_decode(x, w, x2=None, w2=None):
+    """fp32 operands at decode shapes (a handful of rows, no gradient: Mamba2.step of a model that runs without autocast, as
+    inference_t2i.py does) -> the 3xTF32 weight-streaming kernel; None when it does not apply."""
+    if _BACKEND != "tc" or not x.is_cuda or x.dtype != torch.float32 or w.dtype != torch.float32:
+        return None
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or (x2 is not None and (x2.requires_grad or w2.requires_grad))):
+        return None
+    x2d = x.reshape(-1, x.shape[-1])
+    x22 = x2.reshape(-1, x2.shape[-1]) if x2 is not None else None
+    if not abi.gemm_f32_decode_ok(x2d, w, x22, w2):
+        return None
+    return abi.gemm_f32_decode(x2d, w, x22, w2).view(*x.shape[:-1], w.shape[0])
+
+
 def linear(x, w, bias=None):
     """F.linear with autocast semantics; bf16 CUDA operands run on the tcgen05 GEMM."""
     ac = _autocast_dtype(x.device.type) if x.is_cuda else None
@@ -113,6 +127,9 @@ def linear(x, w, bias=None):
         x, w = x.to(ac), cast_param(w, ac)
         bias = bias.to(ac) if bias is not None else None
     if not _eligible(x, w):
+        y = _f32_decode(x, w)
+        if y is not None:
+            return y if bias is None else y + bias
         return F.linear(x, w, bias)
     with torch.autocast(x.device.type, enabled=False):
         return _LinearFn.apply(x, w, bias)
@@ -128,6 +145,11 @@ def lora_linear(x, w, bias, lora_a, lora_b, scaling, dropout=None):
         w, lora_a, lora_b = cast_param(w, ac), cast_param(lora_a, ac), cast_param(lora_b, ac)
         bias = bias.to(ac) if bias is not None else None
     if not _eligible(x, w, lora_a, lora_b):
+        if x.is_cuda and x.dtype == torch.float32 and lora_a.shape[0] % 4 == 0:
+            t = F.linear(xd, lora_a) * scaling                       # (.., r): a few hundred kiloflops
+            y = _f32_decode(x, w, t, lora_b)
+            if y is not None:
+                return y if bias is None else y + bias
         return F.linear(x, w, bias) + F.linear(F.linear(xd, lora_a), lora_b) * scaling
     with torch.autocast(x.device.type, enabled=False):
         t = _LinearFn.apply(xd, lora_a, None) * scaling         # (.., r)

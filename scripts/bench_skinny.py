@@ -64,6 +64,18 @@ def main():
             rows.append({"case": name, "M": M, "N": N, "K": K, "ours_us": ours * 1e3, "tile_kernel_us": tile * 1e3, "cublas_us": cub * 1e3,
                          "forced_ksplit_us": forced, "bytes": by, "ours_gbs": by / ours / 1e6, "frac_of_hbm": by / ours / 1e6 / hbm})
             print(rows[-1], file=sys.stderr, flush=True)
+    # fp32 operands (the model as inference_t2i.py runs it): 3xTF32 kernel vs cuBLAS SGEMM
+    for M in (64,):
+        for name, N, K in (("in_proj fp32", 8512, 2048), ("out_proj fp32", 2048, 4096)):
+            ws = [torch.randn(N, K, device=dev) * 0.02 for _ in range(8)]
+            x = torch.randn(M, K, device=dev)
+            out = torch.empty(M, N, device=dev)
+            ours = timed([lambda w=w: _cabi.gemm_f32_decode(x, w, out=out) for w in ws])
+            cub = timed([lambda w=w: torch.mm(x, w.t(), out=out) for w in ws])
+            by = N * K * 4 + M * K * 4 + M * N * 4
+            rows.append({"case": name, "M": M, "N": N, "K": K, "ours_us": ours * 1e3, "cublas_us": cub * 1e3, "bytes": by,
+                         "ours_gbs": by / ours / 1e6, "frac_of_hbm": by / ours / 1e6 / hbm})
+            print(rows[-1], file=sys.stderr, flush=True)
     print(json.dumps({"hbm_gbs": hbm, "rows": rows}))
 
 

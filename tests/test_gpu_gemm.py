@@ -92,6 +92,57 @@ def test_gemm_decode_shapes_stream_the_weights(M, N, K, K2):
     assert torch.equal(o16.cpu(), o32.cpu().to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("M", [1, 5, 64, 128])
+@pytest.mark.parametrize("N,K,K2", [(8512, 2048, 0), (2048, 4096, 0), (8512, 2048, 8), (260, 132, 0), (1000, 1000, 4)])
+def test_gemm_f32_decode_is_fp32_accurate(M, N, K, K2):
+    """omni_gemm_f32_decode: fp32 operands on the tensor cores through the error-compensated 3xTF32 split (csrc/gemm_skinny.cu)
+    - the projections of Mamba2.step when the model runs in fp32, as inference_t2i.py does.  Against an fp64 reference the
+    result must be as good as an fp32 GEMM (north-star tolerance 1e-5; asserted 2e-6), far from plain TF32 (~5e-4)."""
+    from omnimamba_b200 import _cabi
+    g = torch.Generator().manual_seed(N + K + M)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.05
+    ref = x.double() @ w.double().t()
+    extra = ()
+    if K2:
+        t, bl = torch.randn(M, K2, generator=g), torch.randn(N, K2, generator=g) * 0.1
+        ref = ref + t.double() @ bl.double().t()
+        extra = (t.to(DEV), bl.to(DEV))
+    xd, wd = x.to(DEV), w.to(DEV)
+    assert _cabi.gemm_f32_decode_ok(xd, wd, *extra)
+    _cabi.reset_launch_count()
+    out = _cabi.gemm_f32_decode(xd, wd, *extra)
+    torch.cuda.synchronize()
+    assert _cabi.launch_count() == 1
+    e = rel_l2(out.double().cpu(), ref)
+    e_torch = rel_l2((xd @ wd.t() + (extra[0] @ extra[1].t() if K2 else 0)).double().cpu(), ref)
+    print(f"gemm_f32_decode M={M} N={N} K={K} K2={K2}: rel_l2 vs fp64 {e:.2e} (torch fp32 matmul: {e_torch:.2e})")
+    assert e <= 2e-6, e
+
+
+def test_linear_fp32_decode_uses_the_tf32x3_kernel():
+    """interface.gemm.linear / lora_linear on fp32 CUDA tensors without gradients at a decode shape run on libomnissm, and
+    agree with F.linear to fp32 accuracy; with gradients enabled the call stays on torch (no backward for this kernel)."""
+    from omnimamba_b200 import _cabi
+    from omnimamba_b200.interface.gemm import linear, lora_linear
+    g = torch.Generator().manual_seed(3)
+    x, w = torch.randn(64, 1, 2048, generator=g).to(DEV), (torch.randn(8512, 2048, generator=g) * 0.02).to(DEV)
+    la, lb = (torch.randn(8, 2048, generator=g) * 0.02).to(DEV), (torch.randn(8512, 8, generator=g) * 0.05).to(DEV)
+    with torch.no_grad():
+        _cabi.reset_launch_count()
+        y = linear(x, w)
+        y2 = lora_linear(x, w, None, la, lb, 4.0)
+        n = _cabi.launch_count()
+    assert n == 2
+    ref = F.linear(x.double(), w.double())
+    ref2 = ref + F.linear(F.linear(x.double(), la.double()), lb.double()) * 4.0
+    assert rel_l2(y.double(), ref) <= 2e-6 and rel_l2(y2.double(), ref2) <= 2e-6
+    _cabi.reset_launch_count()
+    xg = x.clone().requires_grad_()
+    linear(xg, w).sum().backward()
+    assert _cabi.launch_count() == 0 and xg.grad is not None
+
+
 def test_gemm_second_operand_pair_is_lora():
     """out = x W^T + t B^T in one accumulator (the LoRA branch of in_proj, lora.py:263-279): d_model=2048 -> 8512, r = 8."""
     from omnimamba_b200 import _cabi
