@@ -244,6 +244,11 @@ constexpr int SF_BK = 32;                                   // fp32 elements per
 constexpr uint32_t SF_W_BYTES = 128 * SF_BK * 4;            // 16 KB
 enum { SFB_FULL = 0, SFB_SPLIT = 4, SFB_EMPTY = 8, SFB_ACCF = 12, SFB_ACCE = 14, SFB_COUNT = 16 };
 constexpr uint32_t kTf32Mask = 0xFFFFE000u;
+#ifndef OMNI_SF_SPLIT_WARPS
+#define OMNI_SF_SPLIT_WARPS 8
+#endif
+constexpr int SF_SPLIT_WARPS = OMNI_SF_SPLIT_WARPS;    // warps that split tiles (the first four also own the TMEM lanes)
+constexpr int SF_THREADS = 64 + 32 * SF_SPLIT_WARPS;
 __device__ __forceinline__ void mma_ss_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -258,7 +263,7 @@ __device__ __forceinline__ void tf32_split(uint32_t a, uint32_t& hi, uint32_t& l
 }
 
 template <int MT, int kStages>
-__global__ void __launch_bounds__(SK_THREADS, 1)
+__global__ void __launch_bounds__(SF_THREADS, 1)
 gemm_skinny_f32_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapX1,
                        const __grid_constant__ CUtensorMap mapW2, const __grid_constant__ CUtensorMap mapX2, SkinnyArgs a) {
   constexpr uint32_t X_BYTES = MT * SF_BK * 4, STAGE = 2 * SF_W_BYTES + 2 * X_BYTES;
@@ -277,13 +282,13 @@ gemm_skinny_f32_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_c
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&bars[SFB_FULL + i], 1);
-      mbar_init(&bars[SFB_SPLIT + i], 4);
+      mbar_init(&bars[SFB_SPLIT + i], SF_SPLIT_WARPS);
       mbar_init(&bars[SFB_EMPTY + i], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars[SFB_ACCF + i], 1); mbar_init(&bars[SFB_ACCE + i], 4); }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 2 * MT);
+  if (warp == 1) tmem_alloc(tmem_ptr, 4 * MT);   // two accumulation buffers of 2 MT columns (hi x hi + lo x hi | hi x lo)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapX1);
     if (a.K2 > 0) { tma_prefetch_desc(&mapW2); tma_prefetch_desc(&mapX2); }
@@ -330,6 +335,7 @@ gemm_skinny_f32_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_c
     // ============ MMA issuer: D[n][m] += W_hi X_hi + W_lo X_hi + W_hi X_lo ====================================================
     const bool leader = sk_elect();
     const uint32_t idesc = make_idesc(128, MT, 2, 2, kMajorK, kMajorK);   // (a / b format 2 = TF32)
+    const uint32_t idesc2 = make_idesc(128, 2 * MT, 2, 2, kMajorK, kMajorK);
     for (int it = 0; it < nsteps; ++it) {
       const int s = it % kStages, ph = (it / kStages) & 1;
       const int grp = it / G, buf = grp & 1;
@@ -340,24 +346,28 @@ gemm_skinny_f32_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_c
       }
       mbar_wait(&bars[SFB_SPLIT + s], ph);
       tc_fence_after();
-      const uint32_t acc = tb + (uint32_t)buf * MT;
+      const uint32_t acc = tb + (uint32_t)buf * 2 * MT;
       const uint32_t sa = smem_u32(smem + s * STAGE);
       const uint64_t dWh = make_sdesc(sa, 16, 1024), dWl = make_sdesc(sa + OFF_WLO, 16, 1024);
       const uint64_t dXh = make_sdesc(sa + OFF_XHI, 16, 1024), dXl = make_sdesc(sa + OFF_XLO, 16, 1024);
+      // Per K = 8 step (32 bytes): W_hi [X_hi ; X_lo]^T as ONE MMA of N = 2 MT (the X_hi and X_lo tiles are adjacent rows of one
+      // swizzled tile) into columns [0, 2 MT), then W_lo X_hi^T into columns [0, MT): two instructions instead of three - these
+      // small MMAs cost ~their issue overhead, not their flops (measured: 12 per stage paced the kernel, not the weight stream).
 #pragma unroll
-      for (uint32_t k = 0; k < SF_BK / 8; ++k) {   // K = 8 per instruction = 32 bytes; the small terms first
-        if (leader) mma_ss_tf32(acc, dWl + k * 2, dXh + k * 2, idesc, !(first && k == 0));
-        if (leader) mma_ss_tf32(acc, dWh + k * 2, dXl + k * 2, idesc, true);
-        if (leader) mma_ss_tf32(acc, dWh + k * 2, dXh + k * 2, idesc, true);
+      for (uint32_t k = 0; k < SF_BK / 8; ++k) {
+        if (leader) mma_ss_tf32(acc, dWh + k * 2, dXh + k * 2, idesc2, !(first && k == 0));
+        if (leader) mma_ss_tf32(acc, dWl + k * 2, dXh + k * 2, idesc, true);
       }
+      (void)dXl;
       if (leader) mma_commit(&bars[SFB_EMPTY + s]);
       if (leader && (it % G == G - 1 || it == nsteps - 1)) mma_commit(&bars[SFB_ACCF + buf]);
       __syncwarp();
     }
   } else {
     // ============ splitters (warps 2-5): hi in place, lo into the stage's second buffers ==================================
-    const int t = tid - 64;
+    const int t = tid - 64;                 // 0 .. 32 SF_SPLIT_WARPS - 1
     const int q = warp & 3;
+    const bool owner = warp < 6;            // warps 2-5 own the four TMEM lane quadrants: they drain and write the partial tile
     int drained = 0;
     auto drain = [&](int g) {   // finished group g: its accumulator -> the fp32 register sums (round-to-nearest adds)
       const int buf = g & 1;
@@ -365,11 +375,12 @@ gemm_skinny_f32_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_c
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < MT; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_addr(tb, q * 32, buf * MT + c), v);
+        uint32_t v[32], v2[32];
+        tmem_ld32(tmem_addr(tb, q * 32, buf * 2 * MT + c), v);
+        tmem_ld32(tmem_addr(tb, q * 32, buf * 2 * MT + MT + c), v2);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) sum[c + e] += __uint_as_float(v[e]);
+        for (int e = 0; e < 32; ++e) sum[c + e] += __uint_as_float(v[e]) + __uint_as_float(v2[e]);
       }
       tc_fence_before();
       __syncwarp();
@@ -380,32 +391,32 @@ gemm_skinny_f32_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_c
       mbar_wait(&bars[SFB_FULL + s], ph);
       uint8_t* st = smem + s * STAGE;
 #pragma unroll
-      for (int k = 0; k < (int)(SF_W_BYTES / 16 / 128); ++k) {   // 1024 16-byte units of W
-        uint4* ph4 = reinterpret_cast<uint4*>(st) + t + 128 * k;
+      for (int k = 0; k < (int)(SF_W_BYTES / 16 / (32 * SF_SPLIT_WARPS)); ++k) {   // 1024 16-byte units of W
+        uint4* ph4 = reinterpret_cast<uint4*>(st) + t + 32 * SF_SPLIT_WARPS * k;
         uint4 v = *ph4, lo;
         tf32_split(v.x, v.x, lo.x); tf32_split(v.y, v.y, lo.y); tf32_split(v.z, v.z, lo.z); tf32_split(v.w, v.w, lo.w);
         *ph4 = v;
-        *(reinterpret_cast<uint4*>(st + OFF_WLO) + t + 128 * k) = lo;
+        *(reinterpret_cast<uint4*>(st + OFF_WLO) + t + 32 * SF_SPLIT_WARPS * k) = lo;
       }
 #pragma unroll
-      for (int k = 0; k < (int)(X_BYTES / 16 / 128); ++k) {
-        uint4* ph4 = reinterpret_cast<uint4*>(st + OFF_XHI) + t + 128 * k;
+      for (int k = 0; k < (int)(X_BYTES / 16 / (32 * SF_SPLIT_WARPS)); ++k) {
+        uint4* ph4 = reinterpret_cast<uint4*>(st + OFF_XHI) + t + 32 * SF_SPLIT_WARPS * k;
         uint4 v = *ph4, lo;
         tf32_split(v.x, v.x, lo.x); tf32_split(v.y, v.y, lo.y); tf32_split(v.z, v.z, lo.z); tf32_split(v.w, v.w, lo.w);
         *ph4 = v;
-        *(reinterpret_cast<uint4*>(st + OFF_XLO) + t + 128 * k) = lo;
+        *(reinterpret_cast<uint4*>(st + OFF_XLO) + t + 32 * SF_SPLIT_WARPS * k) = lo;
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[SFB_SPLIT + s]);
       // (the groups before the one this stage belongs to have all their MMAs issued: drain them while the stream goes on)
-      while (drained < it / G) drain(drained++);
+      if (owner) while (drained < it / G) drain(drained++);
     }
-    while (drained < ngroups) drain(drained++);
+    if (owner) while (drained < ngroups) drain(drained++);
   }
   // ============ epilogue (warps 2-5): partial tile -> shared memory [m][n], cluster reduction -> C (as the bf16 kernel) =====
   float* part = reinterpret_cast<float*>(smem);
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     // (every MMA of this CTA is complete - the last group has been drained - so the stage ring is free for the partial tile)
     const int n = (warp & 3) * 32 + lane;
 #pragma unroll
@@ -414,7 +425,7 @@ gemm_skinny_f32_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_c
   tc_fence_before();
   if (a.ksplit > 1) sk_cluster_sync(); else __syncthreads();
   pdl_wait();
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     const int t = tid - 64;
     const int rows = (MT + a.ksplit - 1) / a.ksplit, m_lo = (int)rank * rows, m_hi = min(min(m_lo + rows, MT), a.M);
     if (a.ksplit == 1) sk_reduce_rows<1>(part, t, (int)rank, m_lo, m_hi, n0, a);
@@ -422,7 +433,7 @@ gemm_skinny_f32_kernel(const __grid_constant__ CUtensorMap mapW1, const __grid_c
     else sk_reduce_rows<4>(part, t, (int)rank, m_lo, m_hi, n0, a);
   }
   if (a.ksplit > 1) sk_cluster_sync(); else __syncthreads();
-  if (warp == 1) tmem_dealloc(tb, 2 * MT);
+  if (warp == 1) tmem_dealloc(tb, 4 * MT);
 }
 }  // namespace
 int g_skinny_ksplit = 0;
@@ -525,7 +536,7 @@ int gemm_skinny_f32(const omni_gemm_params_t* p, cudaStream_t s) {
     cudaFuncSetAttribute(gemm_skinny_f32_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM);
     cudaFuncSetAttribute(gemm_skinny_f32_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM);
   });
-  const dim3 grid((unsigned)(tiles_n * ksplit)), block(SK_THREADS);
+  const dim3 grid((unsigned)(tiles_n * ksplit)), block(SF_THREADS);
   cudaError_t e = MT == 64 ? launch_pdl(kPdlGemm, gemm_skinny_f32_kernel<64, 4>, grid, block, SK_SMEM, s, (unsigned)ksplit, mW1, mX1, mW2, mX2, a)
                            : launch_pdl(kPdlGemm, gemm_skinny_f32_kernel<128, 3>, grid, block, SK_SMEM, s, (unsigned)ksplit, mW1, mX1, mW2, mX2, a);
   if (e != cudaSuccess) return set_error(OMNI_CUDA_ERROR, "gemm_skinny_f32_kernel launch: %s", cudaGetErrorString(e));
