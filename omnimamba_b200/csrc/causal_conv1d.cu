@@ -155,58 +155,128 @@ template <> __device__ __forceinline__ uint2 pack4<__half>(const float (&o)[4]) 
   return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
 
+// packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 operations per issue slot, each lane an ordinary IEEE operation).
+// The 16-bit fast kernels below are bound by instruction issue before HBM (forward 15 instructions per element at 74 % of the
+// roofline, backward 35 at 49 %), so their arithmetic runs on PAIRS of channels, the sigmoid is ex2.approx.ftz + rcp.approx.ftz
+// (no denormal fix-up code) and addresses are 32-bit multiples of the row pitch added to one 64-bit base per batch.
+__device__ __forceinline__ float2 fma2p(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2p(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 add2p(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float ex2_ftz(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float rcp_ftz(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+// d/dv [v sigmoid(v)] = s (1 + v (1 - s)) for a pair of channels
+__device__ __forceinline__ float2 dsilu2(float2 v) {
+  const float2 one = make_float2(1.f, 1.f);
+  const float2 nl = mul2p(v, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 d = add2p(make_float2(ex2_ftz(nl.x), ex2_ftz(nl.y)), one);
+  const float2 s = make_float2(rcp_ftz(d.x), rcp_ftz(d.y));
+  const float2 oms = fma2p(s, make_float2(-1.f, -1.f), one);
+  return mul2p(s, fma2p(v, oms, one));
+}
+template <typename T> __device__ __forceinline__ void unpack22(uint2 r, float2 (&o)[2]);
+template <> __device__ __forceinline__ void unpack22<__nv_bfloat16>(uint2 r, float2 (&o)[2]) {
+  o[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+  o[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+}
+template <> __device__ __forceinline__ void unpack22<__half>(uint2 r, float2 (&o)[2]) {
+  o[0] = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+  o[1] = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+}
+template <typename T> __device__ __forceinline__ uint2 pack22(const float2 (&o)[2]);
+template <> __device__ __forceinline__ uint2 pack22<__nv_bfloat16>(const float2 (&o)[2]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(o[0].x, o[0].y), b = __floats2bfloat162_rn(o[1].x, o[1].y);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+template <> __device__ __forceinline__ uint2 pack22<__half>(const float2 (&o)[2]) {
+  const __half2 a = __floats2half2_rn(o[0].x, o[0].y), b = __floats2half2_rn(o[1].x, o[1].y);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+
+// v sigmoid(v) for a pair of channels
+__device__ __forceinline__ float2 silu2(float2 v) {
+  const float2 nl = mul2p(v, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 d = add2p(make_float2(ex2_ftz(nl.x), ex2_ftz(nl.y)), make_float2(1.f, 1.f));
+  return mul2p(v, make_float2(rcp_ftz(d.x), rcp_ftz(d.y)));
+}
+
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(32 * kSegs, 6) conv1d_fwd_fast_kernel(ConvArgs a) {
   const int d0 = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int b = blockIdx.z;
   const int t0 = (blockIdx.y * kSegs + threadIdx.y) * kTLF;
   if (d0 >= a.D || t0 >= a.L) return;
-  float w[4][4], bia[4];  // w[k][v]: tap k (k = 3 multiplies the current token) of channel d0 + v
+  float2 w[4][2], bia[2];  // w[k][pair]: tap k (k = 3 multiplies the current token) of channels d0 + 2 pair, + 1
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
+  for (int pr = 0; pr < 2; ++pr) {
+    const int64_t da = d0 + 2 * pr, db = d0 + 2 * pr + 1;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) w[k][v] = ld_any(a.w, a.w_dtype, (d0 + v) * a.ws_d + k * a.ws_w);
-    bia[v] = a.bias ? ld_any(a.bias, a.b_dtype, (d0 + v) * a.bs_d) : 0.f;
+    for (int k = 0; k < 4; ++k)
+      w[k][pr] = make_float2(ld_any(a.w, a.w_dtype, da * a.ws_d + k * a.ws_w), ld_any(a.w, a.w_dtype, db * a.ws_d + k * a.ws_w));
+    bia[pr] = a.bias ? make_float2(ld_any(a.bias, a.b_dtype, da * a.bs_d), ld_any(a.bias, a.b_dtype, db * a.bs_d)) : make_float2(0.f, 0.f);
   }
-  const T* xp = static_cast<const T*>(a.x) + b * a.xs_b + d0 + (int64_t)t0 * a.xs_l;
-  T* op = static_cast<T*>(a.out) + b * a.os_b + d0 + (int64_t)t0 * a.os_l;
-  float p1[4], p2[4], p3[4];  // x[t-1], x[t-2], x[t-3]
+  const int xsl = (int)a.xs_l, osl = (int)a.os_l;   // (row pitches fit 32 bits: checked by the host)
+  const T* xp = static_cast<const T*>(a.x) + b * a.xs_b + d0 + (int64_t)t0 * xsl;
+  T* op = static_cast<T*>(a.out) + b * a.os_b + d0 + (int64_t)t0 * osl;
+  float2 p1[2], p2[2], p3[2];  // x[t-1], x[t-2], x[t-3]
   {
     const uint2 z2 = make_uint2(0u, 0u);
-    unpack4<T>(t0 >= 1 ? __ldg(reinterpret_cast<const uint2*>(xp - a.xs_l)) : z2, p1);
-    unpack4<T>(t0 >= 2 ? __ldg(reinterpret_cast<const uint2*>(xp - 2 * a.xs_l)) : z2, p2);
-    unpack4<T>(t0 >= 3 ? __ldg(reinterpret_cast<const uint2*>(xp - 3 * a.xs_l)) : z2, p3);
+    unpack22<T>(t0 >= 1 ? __ldg(reinterpret_cast<const uint2*>(xp - xsl)) : z2, p1);
+    unpack22<T>(t0 >= 2 ? __ldg(reinterpret_cast<const uint2*>(xp - 2 * xsl)) : z2, p2);
+    unpack22<T>(t0 >= 3 ? __ldg(reinterpret_cast<const uint2*>(xp - 3 * xsl)) : z2, p3);
   }
   auto token = [&](uint2 raw, T* dst) {
-    float c[4], acc[4];
-    unpack4<T>(raw, c);
+    float2 c[2], acc[2];
+    unpack22<T>(raw, c);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      acc[v] = fmaf(w[3][v], c[v], fmaf(w[2][v], p1[v], fmaf(w[1][v], p2[v], fmaf(w[0][v], p3[v], bia[v]))));
-      if (SILU) acc[v] = silu_f(acc[v]);
-      p3[v] = p2[v]; p2[v] = p1[v]; p1[v] = c[v];
+    for (int pr = 0; pr < 2; ++pr) {
+      acc[pr] = fma2p(w[3][pr], c[pr], fma2p(w[2][pr], p1[pr], fma2p(w[1][pr], p2[pr], fma2p(w[0][pr], p3[pr], bia[pr]))));
+      if (SILU) acc[pr] = silu2(acc[pr]);
+      p3[pr] = p2[pr]; p2[pr] = p1[pr]; p1[pr] = c[pr];
     }
-    *reinterpret_cast<uint2*>(dst) = pack4<T>(acc);
+    *reinterpret_cast<uint2*>(dst) = pack22<T>(acc);
   };
   const int n = min(kTLF, a.L - t0);
   int i = 0;
 #pragma unroll 1
   for (; i + 16 <= n; i += 16) {  // 16 tokens (128 B per thread) in flight: ~100 KB per SM at 24 resident warps
+    const T* px = xp + (int64_t)i * xsl;
+    T* po = op + (int64_t)i * osl;
     uint2 raw[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) raw[u] = __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(i + u) * a.xs_l));
+    for (int u = 0; u < 16; ++u) raw[u] = __ldg(reinterpret_cast<const uint2*>(px + u * xsl));
 #pragma unroll
-    for (int u = 0; u < 16; ++u) token(raw[u], op + (int64_t)(i + u) * a.os_l);
+    for (int u = 0; u < 16; ++u) token(raw[u], po + u * osl);
   }
 #pragma unroll 1
   for (; i + 8 <= n; i += 8) {
+    const T* px = xp + (int64_t)i * xsl;
+    T* po = op + (int64_t)i * osl;
     uint2 raw[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) raw[u] = __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(i + u) * a.xs_l));
+    for (int u = 0; u < 8; ++u) raw[u] = __ldg(reinterpret_cast<const uint2*>(px + u * xsl));
 #pragma unroll
-    for (int u = 0; u < 8; ++u) token(raw[u], op + (int64_t)(i + u) * a.os_l);
+    for (int u = 0; u < 8; ++u) token(raw[u], po + u * osl);
   }
-  for (; i < n; ++i) token(__ldg(reinterpret_cast<const uint2*>(xp + (int64_t)i * a.xs_l)), op + (int64_t)i * a.os_l);
+#pragma unroll 1
+  for (; i < n; ++i) token(__ldg(reinterpret_cast<const uint2*>(xp + (int64_t)i * xsl)), op + (int64_t)i * osl);
 }
 
 template <typename T>
@@ -219,6 +289,8 @@ bool try_launch_fwd_fast(const ConvArgs& a, int W, const omni_tensor_t& x, const
              (t.shape[2] <= 1 || t.stride[2] % 4 == 0);
     };
     if (!ok8(x) || !ok8(o)) return false;
+    auto pitch32 = [](int64_t st) { return st >= 0 && st * 16 < (int64_t)0x7fffffff; };   // (u * pitch, u < 16, is formed in 32 bits)
+    if (!pitch32(a.xs_l) || !pitch32(a.os_l)) return false;
     dim3 block(32, kSegs), grid((a.D + 127) / 128, (a.L + kSegs * kTLF - 1) / (kSegs * kTLF), a.B);
     if (a.silu) conv1d_fwd_fast_kernel<T, true><<<grid, block, 0, s>>>(a);
     else conv1d_fwd_fast_kernel<T, false><<<grid, block, 0, s>>>(a);
@@ -390,97 +462,134 @@ __global__ void __launch_bounds__(32 * kSegs) conv1d_bwd_kernel(ConvArgs a) {
 // last four dc = dout * act'(c) in registers: c[t] is recomputed from the window, dweight / dbias accumulate over the
 // thread's own tokens, dx[t-3] = sum_k w[k] dc[t-k] leaves as soon as its four dc are known (the three tokens past the
 // thread's range are re-read: L2 hits).  Loads of 8 tokens (x and dout) are issued before any of them is used.
+// The kernel is bound by instruction issue, not by HBM (35 instructions per element in the first version: 62 % issue
+// utilisation at 49 % of the HBM roofline), so the arithmetic runs on PAIRS of channels with the packed fp32 instructions
+// (fma / mul / add .f32x2: two lanes per issue slot, each lane an ordinary IEEE operation), the sigmoid is ex2.approx.ftz +
+// rcp.approx.ftz (no denormal fix-up code), addresses are 32-bit multiples of the row pitch added to one 64-bit base per
+// batch, and the tokens that need no edge predicate (own, with a dx row to store) run in a predicate-free loop.
+constexpr int kCB = 8;   // tokens per batch of loads
 template <typename T, bool SILU>
-__global__ void __launch_bounds__(32 * kSegs, 4) conv1d_bwd_fast_kernel(ConvArgs a, int tl) {
+__global__ void __launch_bounds__(32 * kSegs, 4) conv1d_bwd_fast_kernel(ConvArgs a, int tl, const T* __restrict__ xbase, const T* __restrict__ gbase, T* __restrict__ dxbase) {
+  // (x / dout / dx also arrive as __restrict__ parameters: without the no-alias guarantee every load of the next batch is kept
+  // behind the dx stores of the current one, i.e. at the end of the loop body, and its latency is exposed)
   __shared__ float red[kSegs][32][21];
   const int d0 = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int b = blockIdx.z;
   const int t0 = (blockIdx.y * kSegs + threadIdx.y) * tl;
   const bool active = d0 < a.D && t0 < a.L;
-  float dwa[4][4], dba[4];
+  const float2 zero2 = make_float2(0.f, 0.f);
+  float2 dwa[4][2], dba[2];   // [tap][channel pair]
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    dba[v] = 0.f;
+  for (int pr = 0; pr < 2; ++pr) {
+    dba[pr] = zero2;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dwa[k][v] = 0.f;
+    for (int k = 0; k < 4; ++k) dwa[k][pr] = zero2;
   }
   if (active) {
-    float w[4][4], bia[4];
+    float2 w[4][2], bia[2];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
+    for (int pr = 0; pr < 2; ++pr) {
+      const int64_t da = d0 + 2 * pr, db = d0 + 2 * pr + 1;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) w[k][v] = ld_any(a.w, a.w_dtype, (d0 + v) * a.ws_d + k * a.ws_w);
-      bia[v] = a.bias ? ld_any(a.bias, a.b_dtype, (d0 + v) * a.bs_d) : 0.f;
+      for (int k = 0; k < 4; ++k)
+        w[k][pr] = make_float2(ld_any(a.w, a.w_dtype, da * a.ws_d + k * a.ws_w), ld_any(a.w, a.w_dtype, db * a.ws_d + k * a.ws_w));
+      bia[pr] = a.bias ? make_float2(ld_any(a.bias, a.b_dtype, da * a.bs_d), ld_any(a.bias, a.b_dtype, db * a.bs_d)) : zero2;
     }
-    const T* xp = static_cast<const T*>(a.x) + b * a.xs_b + d0;
-    const T* gp = static_cast<const T*>(a.dout) + b * a.gs_b + d0;
-    T* dxp = static_cast<T*>(a.dx) + b * a.ds_b + d0;
+    const T* __restrict__ xp = xbase + b * a.xs_b + d0;
+    const T* __restrict__ gp = gbase + b * a.gs_b + d0;
+    T* __restrict__ dxp = dxbase + b * a.ds_b + d0;
+    const int xsl = (int)a.xs_l, gsl = (int)a.gs_l, dsl = (int)a.ds_l;   // (row pitches fit 32 bits: checked by the host)
     const uint2 z2 = make_uint2(0u, 0u);
-    float p1[4], p2[4], p3[4];     // x[t-1], x[t-2], x[t-3]
-    float g1[4], g2[4], g3[4];     // dc[t-1], dc[t-2], dc[t-3]
-    unpack4<T>(t0 >= 1 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 1) * a.xs_l)) : z2, p1);
-    unpack4<T>(t0 >= 2 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 2) * a.xs_l)) : z2, p2);
-    unpack4<T>(t0 >= 3 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 3) * a.xs_l)) : z2, p3);
+    float2 p1[2], p2[2], p3[2];     // x[t-1], x[t-2], x[t-3]
+    float2 g1[2], g2[2], g3[2];     // dc[t-1], dc[t-2], dc[t-3]
+    unpack22<T>(t0 >= 1 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 1) * xsl)) : z2, p1);
+    unpack22<T>(t0 >= 2 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 2) * xsl)) : z2, p2);
+    unpack22<T>(t0 >= 3 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 3) * xsl)) : z2, p3);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) g1[v] = g2[v] = g3[v] = 0.f;
+    for (int pr = 0; pr < 2; ++pr) g1[pr] = g2[pr] = g3[pr] = zero2;
     const int own_end = min(t0 + tl, a.L);
     const int tlast = own_end + 3;   // exclusive; dc beyond L is zero
-    auto token = [&](int t, uint2 rx, uint2 rg) {
-      float c[4], g[4];
-      unpack4<T>(rx, c);
-      unpack4<T>(rg, g);
-      const bool own = t < own_end;
+    // one token: `own` = its dc feeds this thread's dweight / dbias sums, `store` = dx[t - 3] is a row of this thread
+    auto token = [&](uint2 rx, uint2 rg, bool own, bool store, T* dst) {
+      float2 c[2], g[2], r[2];
+      unpack22<T>(rx, c);
+      unpack22<T>(rg, g);
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
+      for (int pr = 0; pr < 2; ++pr) {
         if (SILU) {
-          const float pre = fmaf(w[3][v], c[v], fmaf(w[2][v], p1[v], fmaf(w[1][v], p2[v], fmaf(w[0][v], p3[v], bia[v]))));
-          g[v] *= dsilu_f(pre);
+          const float2 pre = fma2p(w[3][pr], c[pr], fma2p(w[2][pr], p1[pr], fma2p(w[1][pr], p2[pr], fma2p(w[0][pr], p3[pr], bia[pr]))));
+          g[pr] = mul2p(g[pr], dsilu2(pre));
         }
         if (own) {
-          dba[v] += g[v];
-          dwa[3][v] = fmaf(g[v], c[v], dwa[3][v]);
-          dwa[2][v] = fmaf(g[v], p1[v], dwa[2][v]);
-          dwa[1][v] = fmaf(g[v], p2[v], dwa[1][v]);
-          dwa[0][v] = fmaf(g[v], p3[v], dwa[0][v]);
+          dba[pr] = add2p(dba[pr], g[pr]);
+          dwa[3][pr] = fma2p(g[pr], c[pr], dwa[3][pr]);
+          dwa[2][pr] = fma2p(g[pr], p1[pr], dwa[2][pr]);
+          dwa[1][pr] = fma2p(g[pr], p2[pr], dwa[1][pr]);
+          dwa[0][pr] = fma2p(g[pr], p3[pr], dwa[0][pr]);
         }
+        r[pr] = fma2p(w[0][pr], g[pr], fma2p(w[1][pr], g1[pr], fma2p(w[2][pr], g2[pr], mul2p(w[3][pr], g3[pr]))));
+        p3[pr] = p2[pr]; p2[pr] = p1[pr]; p1[pr] = c[pr];
+        g3[pr] = g2[pr]; g2[pr] = g1[pr]; g1[pr] = g[pr];
       }
-      const int sidx = t - 3;
-      if (sidx >= t0) {  // (sidx < own_end always holds: t < own_end + 3)
-        float r[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) r[v] = fmaf(w[0][v], g[v], fmaf(w[1][v], g1[v], fmaf(w[2][v], g2[v], w[3][v] * g3[v])));
-        *reinterpret_cast<uint2*>(dxp + (int64_t)sidx * a.ds_l) = pack4<T>(r);
-      }
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        p3[v] = p2[v]; p2[v] = p1[v]; p1[v] = c[v];
-        g3[v] = g2[v]; g2[v] = g1[v]; g1[v] = g[v];
-      }
+      if (store) *reinterpret_cast<uint2*>(dst) = pack22<T>(r);
+    };
+    auto edge_token = [&](int t) {   // any token of [t0, tlast): loads guarded by L, flags from its position
+      const bool in = t < a.L;
+      token(in ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)t * xsl)) : z2,
+            in ? __ldg(reinterpret_cast<const uint2*>(gp + (int64_t)t * gsl)) : z2, t < own_end, t - 3 >= t0,
+            dxp + (int64_t)(t - 3) * dsl);
     };
     int t = t0;
+    const int head_end = min(t0 + 3, tlast);
 #pragma unroll 1
-    for (; t + 8 <= min(tlast, a.L); t += 8) {
-      uint2 rx[8], rg[8];
+    for (; t < head_end; ++t) edge_token(t);   // (the first three tokens have no dx row of this thread behind them)
+    // own tokens with a dx row behind them: no predicates.  The 16 loads of the NEXT batch are issued in the same loop body
+    // (ptxas places loads that nothing in the body consumes at its end whatever the source order - half-batch rotation with a
+    // __syncwarp as a scheduling fence was measured 25 % slower, more registers at 12 warps per SM 5 % slower).
+    if (t + kCB <= own_end) {
+      uint2 rx[kCB], rg[kCB];
+      {
+        const T* px = xp + (int64_t)t * xsl;
+        const T* pg = gp + (int64_t)t * gsl;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        rx[u] = __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t + u) * a.xs_l));
-        rg[u] = __ldg(reinterpret_cast<const uint2*>(gp + (int64_t)(t + u) * a.gs_l));
+        for (int u = 0; u < kCB; ++u) {
+          rx[u] = __ldg(reinterpret_cast<const uint2*>(px + u * xsl));
+          rg[u] = __ldg(reinterpret_cast<const uint2*>(pg + u * gsl));
+        }
       }
+#pragma unroll 1
+      for (; t + 2 * kCB <= own_end; t += kCB) {
+        const T* px = xp + (int64_t)(t + kCB) * xsl;
+        const T* pg = gp + (int64_t)(t + kCB) * gsl;
+        T* pd = dxp + (int64_t)(t - 3) * dsl;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) token(t + u, rx[u], rg[u]);
+        for (int u = 0; u < kCB; ++u) {
+          token(rx[u], rg[u], true, true, pd + u * dsl);
+          rx[u] = __ldg(reinterpret_cast<const uint2*>(px + u * xsl));
+          rg[u] = __ldg(reinterpret_cast<const uint2*>(pg + u * gsl));
+        }
+      }
+      {   // the last full batch
+        T* pd = dxp + (int64_t)(t - 3) * dsl;
+#pragma unroll
+        for (int u = 0; u < kCB; ++u) token(rx[u], rg[u], true, true, pd + u * dsl);
+        t += kCB;
+      }
     }
-    for (; t < tlast; ++t) {
-      const bool in = t < a.L;
-      token(t, in ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)t * a.xs_l)) : z2,
-            in ? __ldg(reinterpret_cast<const uint2*>(gp + (int64_t)t * a.gs_l)) : z2);
-    }
+#pragma unroll 1
+    for (; t < tlast; ++t) edge_token(t);   // (edge tokens in predicated batches of 8: 3 % faster at L = 329, but the extra
+                                            //  live state spills inside the main loop: 6 % slower at L = 4096)
   }
   // reduce dweight / dbias over the block's token segments, then one atomic per (channel, tap)
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
+  for (int pr = 0; pr < 2; ++pr) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) red[threadIdx.y][threadIdx.x][v * 5 + k] = dwa[k][v];
-    red[threadIdx.y][threadIdx.x][v * 5 + 4] = dba[v];
+    for (int k = 0; k < 4; ++k) {
+      red[threadIdx.y][threadIdx.x][(2 * pr) * 5 + k] = dwa[k][pr].x;
+      red[threadIdx.y][threadIdx.x][(2 * pr + 1) * 5 + k] = dwa[k][pr].y;
+    }
+    red[threadIdx.y][threadIdx.x][(2 * pr) * 5 + 4] = dba[pr].x;
+    red[threadIdx.y][threadIdx.x][(2 * pr + 1) * 5 + 4] = dba[pr].y;
   }
   __syncthreads();
   if (threadIdx.y == 0 && d0 < a.D) {
@@ -509,6 +618,8 @@ bool try_launch_bwd_fast(const ConvArgs& a, int W, const omni_tensor_t& x, const
              (t.shape[2] <= 1 || t.stride[2] % 4 == 0);
     };
     if (!ok8(x) || !ok8(g) || !ok8(dx)) return false;
+    auto pitch32 = [](int64_t st) { return st >= 0 && st * 16 < (int64_t)0x7fffffff; };   // (u * pitch, u < 8, is formed in 32 bits)
+    if (!pitch32(a.xs_l) || !pitch32(a.gs_l) || !pitch32(a.ds_l)) return false;
     // tokens per thread: 256 when the sequences are long enough to keep every segment of a block busy with it and there is
     // enough work to fill the GPU (4x fewer partial-sum atomics), else 64 (L = 329, the stage-1 training length, with 256:
     // one segment of 256 tokens, one of 73 and idle ones - the kernel ran at 20 % of the HBM roofline there)
@@ -519,8 +630,11 @@ bool try_launch_bwd_fast(const ConvArgs& a, int W, const omni_tensor_t& x, const
       tl = (a.L + kSegs * nblk - 1) / (kSegs * nblk);
     }
     dim3 block(32, kSegs), grid((unsigned)cols, (a.L + kSegs * tl - 1) / (kSegs * tl), a.B);
-    if (a.silu) conv1d_bwd_fast_kernel<T, true><<<grid, block, 0, s>>>(a, tl);
-    else conv1d_bwd_fast_kernel<T, false><<<grid, block, 0, s>>>(a, tl);
+    const T* xb = static_cast<const T*>(a.x);
+    const T* gb = static_cast<const T*>(a.dout);
+    T* db = static_cast<T*>(a.dx);
+    if (a.silu) conv1d_bwd_fast_kernel<T, true><<<grid, block, 0, s>>>(a, tl, xb, gb, db);
+    else conv1d_bwd_fast_kernel<T, false><<<grid, block, 0, s>>>(a, tl, xb, gb, db);
     return true;
   }
 }
