@@ -116,6 +116,15 @@ def main():
     t = timeit(lambda: layer_norm_fn(xh, w2, None, residual=res, prenorm=True, residual_in_fp32=True, eps=1e-5, is_rms_norm=True))
     by = (B * L) * 2048 * (2 + 4 + 2 + 4)
     out.append(dict(op="layer_norm_fn add+rmsnorm prenorm fwd (65536 rows x 2048)", ms=t * 1e3, bytes=by))
+    # ... and its backward (the training loop): reads the fp32 residual stream, dy (bf16), the incoming residual gradient
+    # (fp32); writes dx (bf16) and the outgoing residual gradient (fp32)
+    xg2, rg2, wg2 = xh.detach().requires_grad_(), res.detach().requires_grad_(), w2.clone().requires_grad_()
+    yn2, ro2 = layer_norm_fn(xg2, wg2, None, residual=rg2, prenorm=True, residual_in_fp32=True, eps=1e-5, is_rms_norm=True)
+    dyn2, dro2 = torch.randn_like(yn2), torch.randn_like(ro2)
+    t = timeit(lambda: torch.autograd.grad((yn2, ro2), (xg2, rg2, wg2), (dyn2, dro2), retain_graph=True))
+    out.append(dict(op="layer_norm_fn add+rmsnorm prenorm bwd (65536 rows x 2048; incl. torch partial-sum reduction)", ms=t * 1e3,
+                    bytes=(B * L) * 2048 * (4 + 2 + 4 + 2 + 4)))
+    del yn2, ro2, dyn2, dro2, xg2, rg2
 
     # a8 selective_state_update, batch 64, fp32 state, stride-0 broadcast operands exactly as Mamba2.step passes them
     Bd = 64
