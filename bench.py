@@ -310,10 +310,20 @@ def main():
     if not args.no_bwd:
         dy = torch.randn(batch, L, H, P, device=device, dtype=torch.bfloat16)
 
+        # as the autograd function runs the pair: the forward of a call that will be differentiated also keeps the fp16 chunk
+        # states (omnissm.h: chunk_states) and the backward reads them instead of re-running its forward state sweep
+        from omnimamba_b200.interface.ssd_combined import _alloc_chunk_states
+        cs = _alloc_chunk_states(batch, L, H, P, N, device, torch.bfloat16) if args.algo != "recurrent" else None
+
         def fwd_bwd():
-            fwd()
+            kept = None
+            if cs is not None:
+                kept = ssd_fwd_raw(dev["x"], dev["dt"], dev["A"], dev["B"], dev["C"], 256, D=dev["D"], dt_bias=dev["dt_bias"],
+                                   dt_softplus=True, out=out, algo=args.algo, chunk_states=cs)[2]
+            else:
+                fwd()
             r = ssd_bwd_raw(dy, dev["x"], dev["dt"], dev["A"], dev["B"], dev["C"], 256, D=dev["D"], dt_bias=dev["dt_bias"],
-                            dt_softplus=True, algo=args.algo)
+                            dt_softplus=True, algo=args.algo, chunk_states=kept)
             if dist_on:  # DDP semantics: only parameter gradients (dA, dD, ddt_bias) cross NVLink
                 allreduce_param_grads([r[2], r[5], r[7]])
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OMNI_ABI_VERSION 7
+#define OMNI_ABI_VERSION 8
 #if defined(__GNUC__)
 #define OMNI_API __attribute__((visibility("default")))
 #else
@@ -117,6 +117,12 @@ typedef struct omni_ssd_fwd_params {
                             * tensor-core algorithm (AUTO falls back to the recurrence without it).  It holds the fp16
                             * copies of B and C and the fp32 state hand-off slots + flags of the half-item schedule
                             * (the flags are reset by a memset on `stream` inside the call); contents are scratch */
+  omni_tensor_t chunk_states; /* optional OUTPUT for a caller that will run the backward (upstream's autograd function
+                            * recomputes the chunk states in its backward; with 180 GB of HBM they can be kept instead):
+                            * 1-D fp16, >= omni_ssd_chunk_states_bytes() bytes, 16B aligned.  When
+                            * omni_ssd_fwd_saves_chunk_states(p) is 1 the forward also stores the state ENTERING every
+                            * 128-token chunk, (B, ceil(L / 128), H * P, N) fp16 - the tile it converts for its own use anyway -
+                            * and the backward given the same tensor skips its forward state sweep.  Absent: nothing changes */
   int32_t chunk_size; /* accepted for API parity; the result does not depend on it */
   int32_t dt_softplus;
   float dt_min, dt_max; /* dt_limit */
@@ -128,6 +134,10 @@ OMNI_API int omni_ssd_fwd_tc_supported(const omni_ssd_fwd_params_t* p);
 OMNI_API int64_t omni_ssd_fwd_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim,
                                               int64_t ngroups, int64_t dstate);
 OMNI_API int omni_ssd_chunk_scan_fwd(const omni_ssd_fwd_params_t* p, void* stream);
+/* bytes of `chunk_states` for these sizes (0: geometry without a tensor-core path) and whether omni_ssd_chunk_scan_fwd
+ * called with exactly these params fills it (tensor-core path taken, plain - not piece - schedule, tensor large enough) */
+OMNI_API int64_t omni_ssd_chunk_states_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim, int64_t dstate);
+OMNI_API int omni_ssd_fwd_saves_chunk_states(const omni_ssd_fwd_params_t* p);
 
 /* Backward.  dout like out.  Outputs: dx like x; ddt (B, L, H) in dt's dtype (gradient w.r.t. the RAW dt);
  * dB, dC: (B, L, G, N) FP32, ZEROED by the caller; dz like z (optional); dinitial_states (B,H,P,N) fp32
@@ -142,6 +152,9 @@ typedef struct omni_ssd_bwd_params {
   omni_tensor_t dout, dfinal_states;
   omni_tensor_t dx, ddt, dB, dC, dz, dinitial_states, dA_part, ddt_bias_part, dD_part;
   omni_tensor_t workspace;
+  omni_tensor_t chunk_states; /* optional INPUT: the tensor a forward with omni_ssd_fwd_saves_chunk_states() == 1 filled for the
+                            * same x / dt / A / B / dt_bias / initial_states; the tensor-core backward then skips its forward
+                            * state sweep (the recurrence ignores it) */
   int32_t chunk_size;
   int32_t dt_softplus;
   float dt_min, dt_max;
@@ -299,6 +312,7 @@ OMNI_API void omni_debug_set_pdl(int mask);
 typedef struct omni_split_conv1d_scan_fwd_params {
   omni_tensor_t zxbcdt, conv1d_weight, conv1d_bias, dt_bias, A, D, initial_states, seq_idx, rmsnorm_weight, outproj_weight;
   omni_tensor_t xbc_conv, scan_out, rstd, y, out, final_states, workspace;
+  omni_tensor_t chunk_states; /* optional, handed to the scan: omni_ssd_fwd_params_t.chunk_states */
   int32_t nheads, headdim, ngroups, dstate, chunk_size;
   int32_t activation;       /* omni_activation_t */
   int32_t norm_before_gate;

@@ -49,7 +49,7 @@ class Conv1dUpdate(C.Structure):
 
 class SsdFwd(C.Structure):
     _fields_ = _T("x", "dt", "A", "B", "C", "D", "z", "dt_bias", "initial_states", "seq_idx", "out", "final_states",
-                  "workspace") + [
+                  "workspace", "chunk_states") + [
         ("chunk_size", C.c_int32), ("dt_softplus", C.c_int32), ("dt_min", C.c_float), ("dt_max", C.c_float),
         ("algo", C.c_int32)]
 
@@ -57,7 +57,7 @@ class SsdFwd(C.Structure):
 class SsdBwd(C.Structure):
     _fields_ = _T("x", "dt", "A", "B", "C", "D", "z", "dt_bias", "initial_states", "seq_idx", "out", "dout", "dfinal_states",
                   "dx", "ddt", "dB", "dC", "dz", "dinitial_states", "dA_part", "ddt_bias_part", "dD_part",
-                  "workspace") + [
+                  "workspace", "chunk_states") + [
         ("chunk_size", C.c_int32), ("dt_softplus", C.c_int32), ("dt_min", C.c_float), ("dt_max", C.c_float),
         ("algo", C.c_int32)]
 
@@ -103,7 +103,7 @@ class Gemm(C.Structure):
 
 class SplitConv1dScanFwd(C.Structure):
     _fields_ = _T("zxbcdt", "conv1d_weight", "conv1d_bias", "dt_bias", "A", "D", "initial_states", "seq_idx", "rmsnorm_weight",
-                  "outproj_weight", "xbc_conv", "scan_out", "rstd", "y", "out", "final_states", "workspace") + [
+                  "outproj_weight", "xbc_conv", "scan_out", "rstd", "y", "out", "final_states", "workspace", "chunk_states") + [
         ("nheads", C.c_int32), ("headdim", C.c_int32), ("ngroups", C.c_int32), ("dstate", C.c_int32), ("chunk_size", C.c_int32),
         ("activation", C.c_int32), ("norm_before_gate", C.c_int32), ("algo", C.c_int32),
         ("dt_min", C.c_float), ("dt_max", C.c_float), ("rmsnorm_eps", C.c_float)]
@@ -140,7 +140,7 @@ ENTRY_POINTS = {
     "omni_softmax_ce_bwd": SoftmaxCe,
 }
 OTHER_SYMBOLS = ["omni_version", "omni_last_error", "omni_launch_count", "omni_reset_launch_count",
-                 "omni_ssd_bwd_workspace_elems", "omni_selective_scan_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint", "omni_debug_set_bwd_trace", "omni_debug_set_handoff", "omni_gemm_bf16_supported", "omni_debug_set_gemm_mode", "omni_debug_set_pdl", "omni_ssd_bwd_tc_supported", "omni_ssd_fwd_tc_supported"]
+                 "omni_ssd_bwd_workspace_elems", "omni_selective_scan_bwd_workspace_elems", "omni_ssd_bwd_tc_workspace_bytes", "omni_ssd_fwd_workspace_bytes", "omni_selftest", "omni_debug_set_trace", "omni_debug_tmem_bench", "omni_debug_set_mbar_hint", "omni_debug_set_bwd_trace", "omni_debug_set_handoff", "omni_gemm_bf16_supported", "omni_debug_set_gemm_mode", "omni_debug_set_pdl", "omni_ssd_bwd_tc_supported", "omni_ssd_fwd_tc_supported", "omni_ssd_chunk_states_bytes", "omni_ssd_fwd_saves_chunk_states"]
 
 # OMNI_LIB_PATH: A/B experiments only (a second build of the same library, e.g. scripts/ab_build.sh); the product path is
 # the in-tree lib/libomnissm.so
@@ -185,6 +185,10 @@ def lib() -> C.CDLL:
     l.omni_ssd_bwd_tc_supported.restype = C.c_int
     l.omni_ssd_fwd_tc_supported.argtypes = [C.POINTER(SsdFwd)]
     l.omni_ssd_fwd_tc_supported.restype = C.c_int
+    l.omni_ssd_chunk_states_bytes.argtypes = [C.c_int64] * 5
+    l.omni_ssd_chunk_states_bytes.restype = C.c_int64
+    l.omni_ssd_fwd_saves_chunk_states.argtypes = [C.POINTER(SsdFwd)]
+    l.omni_ssd_fwd_saves_chunk_states.restype = C.c_int
     l.omni_debug_set_gemm_mode.argtypes = [C.c_int]
     l.omni_debug_set_gemm_mode.restype = None
     l.omni_debug_set_pdl.argtypes = [C.c_int]
@@ -258,6 +262,10 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     lib().omni_reset_launch_count()
+
+
+def ssd_chunk_states_bytes(batch, seqlen, nheads, headdim, dstate) -> int:
+    return int(lib().omni_ssd_chunk_states_bytes(batch, seqlen, nheads, headdim, dstate))
 
 
 def ssd_fwd_workspace_bytes(batch, seqlen, nheads, headdim, ngroups, dstate) -> int:

@@ -77,7 +77,7 @@ extern "C" int omni_split_conv1d_scan_fwd(const omni_split_conv1d_scan_fwd_param
     if (!normed) s.z = heads(cols(zx, 0, dim), H, P);   // no norm: the gate y * silu(z) is applied inside the scan
     s.initial_states = p->initial_states; s.seq_idx = p->seq_idx;
     s.out = heads(p->scan_out, H, P);
-    s.final_states = p->final_states; s.workspace = p->workspace;
+    s.final_states = p->final_states; s.workspace = p->workspace; s.chunk_states = p->chunk_states;
     s.chunk_size = p->chunk_size; s.dt_softplus = 1; s.dt_min = p->dt_min; s.dt_max = p->dt_max; s.algo = p->algo;
     if (int rc = omni_ssd_chunk_scan_fwd(&s, stream)) return rc;
   }

@@ -9,6 +9,8 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s);
 bool ssd_tc_bwd_supported(const omni_ssd_bwd_params_t* p);
 int ssd_tc_bwd(const omni_ssd_bwd_params_t* p, cudaStream_t s);
 int64_t ssd_tc_bwd_workspace_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t ngroups);
+int64_t ssd_tc_chunk_states_bytes(int64_t batch, int64_t seqlen, int64_t nheads);
+bool ssd_tc_fwd_saves_states(const omni_ssd_fwd_params_t* p);
 }  // namespace omni
 
 using namespace omni;
@@ -52,3 +54,13 @@ extern "C" int64_t omni_ssd_bwd_tc_workspace_bytes(int64_t batch, int64_t seqlen
 // workspace size, driver support): the ONE eligibility test - the Python surface asks instead of re-deriving it.
 extern "C" int omni_ssd_bwd_tc_supported(const omni_ssd_bwd_params_t* p) { return p != nullptr && ssd_tc_bwd_supported(p) ? 1 : 0; }
 extern "C" int omni_ssd_fwd_tc_supported(const omni_ssd_fwd_params_t* p) { return p != nullptr && ssd_tc_fwd_supported(p) ? 1 : 0; }
+
+// The optional chunk-state tensor a forward can leave for its backward (omnissm.h: omni_ssd_fwd_params_t.chunk_states).
+extern "C" int64_t omni_ssd_chunk_states_bytes(int64_t batch, int64_t seqlen, int64_t nheads, int64_t headdim, int64_t dstate) {
+  if (headdim != 64 || dstate != 128 || batch <= 0 || seqlen <= 0 || nheads <= 0) return 0;
+  return ssd_tc_chunk_states_bytes(batch, seqlen, nheads);
+}
+extern "C" int omni_ssd_fwd_saves_chunk_states(const omni_ssd_fwd_params_t* p) {
+  if (p == nullptr || p->algo == OMNI_SSD_RECURRENT) return 0;
+  return ssd_tc_fwd_saves_states(p) ? 1 : 0;
+}

@@ -283,8 +283,12 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   auto it_next = [&](ChunkIter& it) {
     if (++it.c == it.cend) it_set(it, it.u + 1);
   };
-  constexpr int mode = MODE;  // (one instantiation per mode: the forward does not carry the sweeps' code and vice versa)
-  constexpr int leadE = MODE == 0 ? kLeadEFwd : kLeadE;
+  // (one instantiation per mode: the forward does not carry the sweeps' code and vice versa.)  MODE 3 = the forward of a caller
+  // that will run the backward: as mode 0, plus the TMA store of the fp16 state entering every chunk (the S16 tile the state
+  // keepers build for Yoff anyway) - what the backward's forward sweep (mode 1) would otherwise recompute.
+  constexpr int mode = MODE == 3 ? 0 : MODE;
+  constexpr bool save = MODE == 3;
+  constexpr int leadE = mode == 0 ? kLeadEFwd : kLeadE;
   auto cphys = [&](int c) { return mode == 2 ? nchunks - 1 - c : c; };  // chunk visited at step c of an item
 
   if (warp == 2) {
@@ -939,8 +943,15 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         named_bar_sync(6, 128);
         const float dch = tab->dchunk[hh];
-        if (mode != 0) {  // state sweeps: the previous TMA store must have read the S16 tile
-          if (w == 0 && lane == 0) tma_store_wait_read<0>();
+        if (mode != 0 || save) {  // state stores: the previous TMA store must have read the S16 tile
+          // (forward with stores: warp 0's lane 0 also commits that warp's y stores - `elect_one` picks lane 0.  With bf16 output
+          // exactly four y groups - the epilogue of chunk gg - 1, always in range for warp 0 - were committed after the state
+          // store of step gg - 1: those may stay pending.  Measured: the forward with stores is 12 % slower than the plain one
+          // either way - the cost is the 32 KB read of the S16 tile beside the MMA's own reads, not this wait)
+          if (w == 0 && lane == 0) {
+            if (save && !kDirectY && a.out_dtype == OMNI_BF16) tma_store_wait_read<4>();
+            else tma_store_wait_read<0>();
+          }
           named_bar_sync(1, 128);
         }
         if (gg > 0) tc_fence_after();
@@ -1033,7 +1044,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         __syncwarp();
         if (w == 0) TR(16);
         if (lane == 0) mbar_arrive(&bars[B_S_READY]);
-        if (mode != 0 && !a.no_store) {  // state sweeps: the state ENTERING this chunk -> workspace[b][chunk][(h,p)][n] (fp16)
+        if ((mode != 0 && !a.no_store) || save) {  // the state ENTERING this chunk -> workspace[b][chunk][(h,p)][n] (fp16)
           named_bar_sync(1, 128);
           if (w == 0 && lane == 0) {
             tma_store_4d(&mapS, smem + SM_S, 0, sn.h0 * HD, cphys(sn.c), sn.b);
@@ -1312,7 +1323,8 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   } else {
     mY = mX;  // unused
   }
-  if (mode != 0 && !no_store) {  // fp16 states: (n 128, rows H*64, chunk, batch), box 64 x 128 rows
+  const bool save = mode == 0 && ws_states != nullptr;   // forward that also stores the chunk states (kernel MODE 3)
+  if ((mode != 0 && !no_store) || save) {  // fp16 states: (n 128, rows H*64, chunk, batch), box 64 x 128 rows
     const uint64_t dims[4] = {(uint64_t)NS, (uint64_t)(H * HD), (uint64_t)nchunks, (uint64_t)Bsz};
     const uint64_t strides[3] = {(uint64_t)NS * 2, (uint64_t)(H * HD * NS) * 2, (uint64_t)(nchunks * H * HD * NS) * 2};
     const uint32_t box[4] = {64, 128, 1, 1};
@@ -1331,6 +1343,7 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
     cudaFuncSetAttribute(ssd_tc_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     cudaFuncSetAttribute(ssd_tc_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     cudaFuncSetAttribute(ssd_tc_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(ssd_tc_fwd_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
   });
   const int nitems = (int)(Bsz * (H / 2));
   const int grid = nitems < sm_count() ? nitems : sm_count();
@@ -1348,11 +1361,12 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
   if (flags != nullptr) {  // hand-off flags of the half-item schedule (a memset node under graph capture)
     if (cudaMemsetAsync(flags, 0, kHandSlots * sizeof(int), s) != cudaSuccess) { flags = nullptr; a.hand = nullptr; a.flags = nullptr; }
   }
-  if (a.trace != nullptr) {  // debug instantiations with the probe sites
+  if (a.trace != nullptr && !save) {  // debug instantiations with the probe sites
     if (mode == 0) ssd_tc_fwd_kernel<0, true><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
     else if (mode == 1) ssd_tc_fwd_kernel<1, true><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
     else ssd_tc_fwd_kernel<2, true><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
-  } else if (mode == 0) ssd_tc_fwd_kernel<0, false><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+  } else if (save) ssd_tc_fwd_kernel<3, false><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
+  else if (mode == 0) ssd_tc_fwd_kernel<0, false><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
   else if (mode == 1) ssd_tc_fwd_kernel<1, false><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
   else ssd_tc_fwd_kernel<2, false><<<grid, kThreads, SMEM_BYTES, s>>>(mX, mB, mC, mY, mS, a);
   OMNI_CUDA_LAUNCH_CHECK("ssd_tc_fwd_kernel");
@@ -1386,6 +1400,17 @@ bool piece_view(const omni_tensor_t& t, int k, omni_tensor_t& v) {
   v.shape[1] = t.shape[1] / k;
   v.stride[0] = v.shape[1] * t.stride[1];
   return true;
+}
+}  // namespace
+
+int64_t ssd_tc_chunk_states_bytes(int64_t batch, int64_t seqlen, int64_t nheads) {
+  return batch * ((seqlen + Q - 1) / Q) * nheads * HD * NS * 2;
+}
+namespace {
+bool chunk_states_ok(const omni_ssd_fwd_params_t* p) {
+  const omni_tensor_t& c = p->chunk_states;
+  if (!present(c) || c.ndim != 1 || c.stride[0] != 1 || c.dtype != OMNI_F16 || !aligned16(c.data)) return false;
+  return c.shape[0] * 2 >= ssd_tc_chunk_states_bytes(p->x.shape[0], p->x.shape[1], p->x.shape[2]);
 }
 }  // namespace
 
@@ -1462,8 +1487,19 @@ int ssd_tc_fwd(const omni_ssd_fwd_params_t* p, cudaStream_t s) {
     }
     return OMNI_OK;
   }
-  return tc_launch(0, x, p->dt, p->A, p->D, p->dt_bias, p->initial_states, p->final_states, o, wsB, wsC, nullptr, G,
-                   p->dt_softplus, p->dt_min, p->dt_max, s, hand, flags);
+  return tc_launch(0, x, p->dt, p->A, p->D, p->dt_bias, p->initial_states, p->final_states, o, wsB, wsC,
+                   chunk_states_ok(p) ? p->chunk_states.data : nullptr, G, p->dt_softplus, p->dt_min, p->dt_max, s, hand, flags);
+}
+
+// 1 when ssd_tc_fwd called with these params fills p->chunk_states (plain schedule only: the piece schedule runs the
+// forward on piece views whose chunk grid need not be the backward's)
+bool ssd_tc_fwd_saves_states(const omni_ssd_fwd_params_t* p) {
+  if (!ssd_tc_fwd_supported(p) || !chunk_states_ok(p)) return false;
+  const omni_tensor_t& x = p->x;
+  int k = piece_count(x.shape[0], x.shape[1], x.shape[2]);
+  omni_tensor_t v;
+  if (k > 1 && !(piece_view(x, k, v) && piece_view(p->dt, k, v) && piece_view(p->out, k, v))) k = 1;
+  return k == 1;
 }
 
 // State sweeps for the backward (ssd_tc_bwd.cu): mode 1 = forward states from (x, fp16 B), mode 2 = reverse sweep of the

@@ -833,8 +833,14 @@ int ssd_tc_bwd(const omni_ssd_bwd_params_t* p, cudaStream_t s) {
   omni_tensor_t none{};
   // forward states S_c (x, B, sj) and reverse state gradients dS_{c+1} (dy, C, exp(lam)); the reverse sweep's final
   // state is dS_0 = the gradient of initial_states
-  if (int rc = ssd_tc_state_sweep(1, x, dt, p->A, p->dt_bias, p->initial_states, none, wsB, wsS, G, p->dt_softplus, p->dt_min,
-                                  p->dt_max, s, hand, piece_ws))
+  // (skipped when the forward left its chunk states - omnissm.h: chunk_states - for this call)
+  const omni_tensor_t& cs = p->chunk_states;
+  const bool have_states = present(cs) && cs.ndim == 1 && cs.stride[0] == 1 && cs.dtype == OMNI_F16 && aligned16(cs.data) &&
+                           cs.shape[0] * 2 >= st_bytes;
+  if (present(cs)) OMNI_CHECK(have_states, OMNI_BAD_SHAPE, "ssd bwd: chunk_states must be the forward's 1-D fp16 tensor");
+  if (have_states) wsS = static_cast<__half*>(cs.data);
+  else if (int rc = ssd_tc_state_sweep(1, x, dt, p->A, p->dt_bias, p->initial_states, none, wsB, wsS, G, p->dt_softplus, p->dt_min,
+                                       p->dt_max, s, hand, piece_ws))
     return rc;
   if (int rc = ssd_tc_state_sweep(2, dy, dt, p->A, p->dt_bias, p->dfinal_states, p->dinitial_states, wsC, wsDS, G, p->dt_softplus,
                                   p->dt_min, p->dt_max, s, hand + ssd_tc_hand_bytes(), piece_ws))

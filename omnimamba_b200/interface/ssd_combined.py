@@ -25,13 +25,28 @@ _DEFAULT_ALGO = os.environ.get("OMNI_SSD_ALGO", "auto")
 assert _DEFAULT_ALGO in _ALGO, f"OMNI_SSD_ALGO must be one of {sorted(_ALGO)}"
 
 
+# A forward that will be followed by a backward also keeps the fp16 state entering every chunk (omnissm.h: chunk_states; +2 H P N
+# bytes per 128 tokens and sequence): the backward then skips its forward state sweep.  OMNI_SSD_SAVE_STATES=0 restores upstream's
+# recompute-everything behaviour (less memory, one more sweep).
+_SAVE_STATES = os.environ.get("OMNI_SSD_SAVE_STATES", "1") != "0"
+
+
+def _alloc_chunk_states(batch, seqlen, nheads, headdim, dstate, device, dtype):
+    if not _SAVE_STATES or dtype != torch.bfloat16 or _DEFAULT_ALGO == "recurrent":
+        return None
+    n = abi.ssd_chunk_states_bytes(batch, seqlen, nheads, headdim, dstate)
+    return torch.empty(n // 2, device=device, dtype=torch.float16) if n > 0 else None
+
+
 def _last_contig(t):
     return t if t is None or t.stride(-1) == 1 else t.contiguous()
 
 
 def ssd_fwd_raw(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initial_states=None, seq_idx=None,
-                dt_softplus=False, dt_limit=(0.0, float("inf")), return_final_states=False, out=None, algo="auto"):
-    """x: (B, L, H, P); dt: (B, L, H); A: (H); B, C: (B, L, G, N).  Returns (out, final_states | None)."""
+                dt_softplus=False, dt_limit=(0.0, float("inf")), return_final_states=False, out=None, algo="auto",
+                chunk_states=None):
+    """x: (B, L, H, P); dt: (B, L, H); A: (H); B, C: (B, L, G, N).  Returns (out, final_states | None); with `chunk_states`
+    (a tensor of _alloc_chunk_states) a third value: that tensor if the forward filled it, else None."""
     batch, seqlen, nheads, headdim = x.shape
     dstate = B.shape[-1]
     if out is None:
@@ -49,13 +64,20 @@ def ssd_fwd_raw(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initia
     p.chunk_size, p.dt_softplus = int(chunk_size), int(bool(dt_softplus))
     p.dt_min, p.dt_max = float(dt_limit[0]), float(min(dt_limit[1], 3.0e38))
     p.algo = _ALGO[_DEFAULT_ALGO if algo == "auto" else algo]
+    if chunk_states is not None:
+        p.chunk_states = abi.tdesc(chunk_states)
+        if not abi.lib().omni_ssd_fwd_saves_chunk_states(abi.C.byref(p)):
+            chunk_states = None
+            p.chunk_states = abi.tdesc(None)
+        abi.call("omni_ssd_chunk_scan_fwd", p, x.device)
+        return out, fin, chunk_states
     abi.call("omni_ssd_chunk_scan_fwd", p, x.device)
     return out, fin
 
 
 def ssd_bwd_raw(dout, x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initial_states=None, seq_idx=None,
                 dt_softplus=False, dt_limit=(0.0, float("inf")), dfinal_states=None, dx=None, ddt=None, dz=None,
-                want_dinitial=False, algo="auto", out=None):
+                want_dinitial=False, algo="auto", out=None, chunk_states=None):
     """Returns dx, ddt (raw), dA (H), dB, dC (fp32, (B,L,G,N)), dD, dz, ddt_bias, dinitial_states.
     bf16 x/B/C/dout with the OmniMamba geometry run on the tensor-core kernels (algo "auto"); `out` is accepted and ignored."""
     batch, seqlen, nheads, headdim = x.shape
@@ -83,6 +105,7 @@ def ssd_bwd_raw(dout, x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, 
     p.dout, p.dfinal_states = abi.tdesc(dout), abi.tdesc(dfinal_states)
     p.dx, p.ddt, p.dB, p.dC, p.dz = (abi.tdesc(t) for t in (dx, ddt, dB, dC, dz))
     p.dinitial_states = abi.tdesc(dinit)
+    p.chunk_states = abi.tdesc(chunk_states)   # (the forward's chunk states, if it kept them: no forward state sweep)
     p.dA_part, p.ddt_bias_part = abi.tdesc(dA_part), abi.tdesc(ddtb_part)
     p.chunk_size, p.dt_softplus = int(chunk_size), int(bool(dt_softplus))
     p.dt_min, p.dt_max = float(dt_limit[0]), float(min(dt_limit[1], 3.0e38))
@@ -143,23 +166,30 @@ class MambaChunkScanCombinedFn(torch.autograd.Function):
         A = A.float().contiguous()
         dt_bias = dt_bias.contiguous() if dt_bias is not None else None
         initial_states = _last_contig(initial_states)
-        out, fin = ssd_fwd_raw(x, dt, A, B, C, chunk_size, D, z, dt_bias, initial_states, seq_idx, dt_softplus,
-                               dt_limit, return_final_states)
-        ctx.save_for_backward(x, dt, A, B, C, D, z, dt_bias, initial_states, seq_idx)
+        cs = None
+        if any(ctx.needs_input_grad) and z is None and seq_idx is None:
+            cs = _alloc_chunk_states(batch, seqlen, nheads, headdim, dstate, x.device, x.dtype)
+        if cs is not None:
+            out, fin, cs = ssd_fwd_raw(x, dt, A, B, C, chunk_size, D, z, dt_bias, initial_states, seq_idx, dt_softplus,
+                                       dt_limit, return_final_states, chunk_states=cs)
+        else:
+            out, fin = ssd_fwd_raw(x, dt, A, B, C, chunk_size, D, z, dt_bias, initial_states, seq_idx, dt_softplus,
+                                   dt_limit, return_final_states)
+        ctx.save_for_backward(x, dt, A, B, C, D, z, dt_bias, initial_states, seq_idx, cs)
         ctx.chunk_size, ctx.dt_softplus, ctx.dt_limit = chunk_size, dt_softplus, dt_limit
         ctx.return_final_states = return_final_states
         return out if not return_final_states else (out, fin)
 
     @staticmethod
     def backward(ctx, dout, *args):
-        x, dt, A, B, C, D, z, dt_bias, initial_states, seq_idx = ctx.saved_tensors
+        x, dt, A, B, C, D, z, dt_bias, initial_states, seq_idx, cs = ctx.saved_tensors
         dfin = args[0] if ctx.return_final_states else None
         if dfin is not None:
             dfin = dfin.float().contiguous()
         dout = _last_contig(dout)
         dx, ddt, dA, dB, dC, dD, dz, ddt_bias, dinit = ssd_bwd_raw(
             dout, x, dt, A, B, C, ctx.chunk_size, D, z, dt_bias, initial_states, seq_idx, ctx.dt_softplus,
-            ctx.dt_limit, dfinal_states=dfin, want_dinitial=initial_states is not None)
+            ctx.dt_limit, dfinal_states=dfin, want_dinitial=initial_states is not None, chunk_states=cs)
         return (dx, ddt, dA, dB.to(B.dtype), dC.to(C.dtype), None,
                 dD.to(D.dtype) if dD is not None else None, dz,
                 ddt_bias.to(dt_bias.dtype) if ddt_bias is not None else None,
@@ -246,6 +276,21 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
         p.rmsnorm_weight, p.outproj_weight = abi.tdesc(rmsnorm_weight), abi.tdesc(w if fuse_gemm else None)
         p.xbc_conv, p.scan_out, p.rstd, p.y, p.out = (abi.tdesc(t) for t in (xBC_conv, scan_out, rstd, y, out))
         p.final_states, p.workspace = abi.tdesc(fin), abi.tdesc(ws)
+        cs = None
+        if any(ctx.needs_input_grad) and rmsnorm_weight is not None and seq_idx is None:
+            cs = _alloc_chunk_states(batch, seqlen, nheads, headdim, dstate, dev, dt_)
+        if cs is not None:   # ask the library whether the scan inside the call will fill it (same views as the C side builds)
+            q = abi.SsdFwd()
+            q.x = abi.tdesc(xBC_conv[..., :dim].view(batch, seqlen, nheads, headdim))
+            q.B = abi.tdesc(xBC_conv[..., dim:dim + ngroups * dstate].view(batch, seqlen, ngroups, dstate))
+            q.C = abi.tdesc(xBC_conv[..., dim + ngroups * dstate:].view(batch, seqlen, ngroups, dstate))
+            q.dt, q.A, q.D, q.dt_bias = abi.tdesc(dt), abi.tdesc(A), abi.tdesc(D), abi.tdesc(dt_bias.contiguous())
+            q.initial_states = abi.tdesc(_last_contig(initial_states))
+            q.out, q.final_states = abi.tdesc(scan_out.view(batch, seqlen, nheads, headdim)), abi.tdesc(fin)
+            q.workspace, q.chunk_states, q.algo = abi.tdesc(ws), abi.tdesc(cs), _ALGO[_DEFAULT_ALGO]
+            if not abi.lib().omni_ssd_fwd_saves_chunk_states(abi.C.byref(q)):
+                cs = None
+        p.chunk_states = abi.tdesc(cs)
         p.nheads, p.headdim, p.ngroups, p.dstate, p.chunk_size = nheads, headdim, ngroups, dstate, int(chunk_size)
         p.activation, p.norm_before_gate, p.algo = act, int(bool(norm_before_gate)), _ALGO[_DEFAULT_ALGO]
         p.dt_min, p.dt_max, p.rmsnorm_eps = float(dt_limit[0]), float(min(dt_limit[1], 3.0e38)), float(rmsnorm_eps)
@@ -265,7 +310,7 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
         else:
             out = y
         ctx.save_for_backward(zxbcdt, conv1d_weight, conv1d_bias, scan_out, A, D, dt_bias, initial_states, seq_idx,
-                              rmsnorm_weight, rstd, outproj_weight, outproj_bias)
+                              rmsnorm_weight, rstd, outproj_weight, outproj_bias, cs)
         ctx.dt_limit, ctx.return_final_states, ctx.act = dt_limit, return_final_states, act
         ctx.rmsnorm_eps, ctx.norm_before_gate, ctx.chunk_size = rmsnorm_eps, norm_before_gate, chunk_size
         ctx.headdim, ctx.ngroups = headdim, ngroups
@@ -274,7 +319,7 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, *args):
         (zxbcdt, conv1d_weight, conv1d_bias, scan_out, A, D, dt_bias, initial_states, seq_idx, rmsnorm_weight, rstd,
-         outproj_weight, outproj_bias) = ctx.saved_tensors
+         outproj_weight, outproj_bias, cs) = ctx.saved_tensors
         dfin = args[0] if ctx.return_final_states else None
         if dfin is not None:
             dfin = dfin.float().contiguous()
@@ -334,7 +379,7 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
             dzscan = dz.view(batch, seqlen, nheads, headdim)
         _, _, dA, dB, dC, dD, _, ddt_bias, dinit = ssd_bwd_raw(
             dscan, x, dt, A, Bm, Cm, ctx.chunk_size, D, zscan, dt_bias, initial_states, seq_idx, True, ctx.dt_limit,
-            dfinal_states=dfin, dx=dx, ddt=ddt, dz=dzscan, want_dinitial=initial_states is not None)
+            dfinal_states=dfin, dx=dx, ddt=ddt, dz=dzscan, want_dinitial=initial_states is not None, chunk_states=cs)
         dxBC_conv[..., dim:dim + ngroups * dstate].copy_(dB.view(batch, seqlen, ngroups * dstate))
         dxBC_conv[..., dim + ngroups * dstate:].copy_(dC.view(batch, seqlen, ngroups * dstate))
         dweight = torch.zeros(conv1d_weight.shape, device=dev, dtype=torch.float32)

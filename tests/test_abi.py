@@ -64,7 +64,7 @@ def test_struct_sizes_match_c_compiler(tmp_path, lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.omni_version() == 7
+    assert lib.omni_version() == 8
     assert isinstance(lib.omni_last_error(), bytes)
 
 
