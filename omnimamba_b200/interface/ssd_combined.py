@@ -29,6 +29,10 @@ assert _DEFAULT_ALGO in _ALGO, f"OMNI_SSD_ALGO must be one of {sorted(_ALGO)}"
 # bytes per 128 tokens and sequence): the backward then skips its forward state sweep.  OMNI_SSD_SAVE_STATES=0 restores upstream's
 # recompute-everything behaviour (less memory, one more sweep).
 _SAVE_STATES = os.environ.get("OMNI_SSD_SAVE_STATES", "1") != "0"
+# The fused path-A node keeps its conv output for the backward as well instead of recomputing it there as upstream does
+# (2 (d_inner + 2 G N) bytes per token and layer: 12 GB over the 48 layers of the stage-1 step, on a 180 GB part);
+# OMNI_KEEP_CONV_OUT=0 restores the recompute.
+_KEEP_CONV = os.environ.get("OMNI_KEEP_CONV_OUT", "1") != "0"
 
 
 def _alloc_chunk_states(batch, seqlen, nheads, headdim, dstate, device, dtype):
@@ -213,8 +217,9 @@ def _autocast_dtype(device_type="cuda"):
 
 class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
     """The training hot op (path A): split zxbcdt -> causal conv1d + SiLU -> SSD scan -> gated RMSNorm -> out_proj
-    in one autograd node.  Saves only zxbcdt, the pre-norm scan output and rstd; backward recomputes the conv
-    output (upstream does the same)."""
+    in one autograd node.  Saves zxbcdt, the pre-norm scan output, rstd and - memory for time on a 180 GB part, both with an
+    environment opt-out - the conv output and the fp16 chunk states of the scan; upstream saves only the first three and
+    recomputes the conv output and the chunk states in its backward."""
 
     @staticmethod
     def forward(ctx, zxbcdt, conv1d_weight, conv1d_bias, dt_bias, A, D, chunk_size, initial_states=None, seq_idx=None,
@@ -310,7 +315,8 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
         else:
             out = y
         ctx.save_for_backward(zxbcdt, conv1d_weight, conv1d_bias, scan_out, A, D, dt_bias, initial_states, seq_idx,
-                              rmsnorm_weight, rstd, outproj_weight, outproj_bias, cs)
+                              rmsnorm_weight, rstd, outproj_weight, outproj_bias, cs,
+                              xBC_conv if (_KEEP_CONV and any(ctx.needs_input_grad)) else None)
         ctx.dt_limit, ctx.return_final_states, ctx.act = dt_limit, return_final_states, act
         ctx.rmsnorm_eps, ctx.norm_before_gate, ctx.chunk_size = rmsnorm_eps, norm_before_gate, chunk_size
         ctx.headdim, ctx.ngroups = headdim, ngroups
@@ -319,7 +325,7 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, *args):
         (zxbcdt, conv1d_weight, conv1d_bias, scan_out, A, D, dt_bias, initial_states, seq_idx, rmsnorm_weight, rstd,
-         outproj_weight, outproj_bias, cs) = ctx.saved_tensors
+         outproj_weight, outproj_bias, cs, xBC_conv) = ctx.saved_tensors
         dfin = args[0] if ctx.return_final_states else None
         if dfin is not None:
             dfin = dfin.float().contiguous()
@@ -334,10 +340,10 @@ class MambaSplitConv1dScanCombinedFn(torch.autograd.Function):
         z = zxbcdt[..., :dim]
         xBC = zxbcdt[..., dim:dim + conv_dim]
         dt = zxbcdt[..., dim + conv_dim:]
-        # recompute the conv output
-        xBC_conv = torch.empty(batch, seqlen, conv_dim, device=dev, dtype=zxbcdt.dtype)
-        conv1d_fwd_raw(xBC.transpose(1, 2), conv1d_weight, conv1d_bias, seq_idx, None, xBC_conv.transpose(1, 2), None,
-                       ctx.act)
+        if xBC_conv is None:   # recompute the conv output (OMNI_KEEP_CONV_OUT=0: upstream's behaviour)
+            xBC_conv = torch.empty(batch, seqlen, conv_dim, device=dev, dtype=zxbcdt.dtype)
+            conv1d_fwd_raw(xBC.transpose(1, 2), conv1d_weight, conv1d_bias, seq_idx, None, xBC_conv.transpose(1, 2), None,
+                           ctx.act)
         x = xBC_conv[..., :dim].view(batch, seqlen, nheads, headdim)
         Bm = xBC_conv[..., dim:dim + ngroups * dstate].view(batch, seqlen, ngroups, dstate)
         Cm = xBC_conv[..., dim + ngroups * dstate:].view(batch, seqlen, ngroups, dstate)
