@@ -467,28 +467,47 @@ __global__ void __launch_bounds__(32 * kSegs) conv1d_bwd_kernel(ConvArgs a) {
 // (fma / mul / add .f32x2: two lanes per issue slot, each lane an ordinary IEEE operation), the sigmoid is ex2.approx.ftz +
 // rcp.approx.ftz (no denormal fix-up code), addresses are 32-bit multiples of the row pitch added to one 64-bit base per
 // batch, and the tokens that need no edge predicate (own, with a dx row to store) run in a predicate-free loop.
-constexpr int kCB = 8;   // tokens per batch of loads
-template <typename T, bool SILU>
-__global__ void __launch_bounds__(32 * kSegs, 4) conv1d_bwd_fast_kernel(ConvArgs a, int tl, const T* __restrict__ xbase, const T* __restrict__ gbase, T* __restrict__ dxbase) {
+// NP channel pairs per thread (2: 8-byte vectors, 1: 4-byte), CB tokens per batch of loads, MINB resident blocks per SM.
+// Measured (profiles/r2c_conv_bwd_channels_ab.txt, (16, 4096)): 4 channels x 8 tokens x 4 blocks 0.383 ms (the default); 2 channels
+// per thread - half the register state, more warps - 0.405 ms at 6 blocks per SM and worse beyond (spills at 72 / 64 registers,
+// 16-token batches 0.47 - 0.55 ms): fewer bytes in flight per warp cost more than the extra warps bring.
+template <int NP> struct RawVec;
+template <> struct RawVec<2> { using type = uint2; };
+template <> struct RawVec<1> { using type = uint32_t; };
+template <typename T, int NP> __device__ __forceinline__ void unpack_np(typename RawVec<NP>::type r, float2 (&o)[NP]) {
+  if constexpr (NP == 2) unpack22<T>(r, o);
+  else { uint2 t = make_uint2(r, 0u); float2 q[2]; unpack22<T>(t, q); o[0] = q[0]; }
+}
+template <typename T, int NP> __device__ __forceinline__ typename RawVec<NP>::type pack_np(const float2 (&o)[NP]) {
+  if constexpr (NP == 2) return pack22<T>(o);
+  else { const float2 q[2] = {o[0], make_float2(0.f, 0.f)}; return pack22<T>(q).x; }
+}
+template <int NP> __device__ __forceinline__ typename RawVec<NP>::type raw_zero() {
+  if constexpr (NP == 2) return make_uint2(0u, 0u); else return 0u;
+}
+template <typename T, bool SILU, int NP, int CB, int MINB>
+__global__ void __launch_bounds__(32 * kSegs, MINB) conv1d_bwd_fast_kernel(ConvArgs a, int tl, const T* __restrict__ xbase, const T* __restrict__ gbase, T* __restrict__ dxbase) {
   // (x / dout / dx also arrive as __restrict__ parameters: without the no-alias guarantee every load of the next batch is kept
   // behind the dx stores of the current one, i.e. at the end of the loop body, and its latency is exposed)
-  __shared__ float red[kSegs][32][21];
-  const int d0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  using Raw = typename RawVec<NP>::type;
+  constexpr int kCB = CB, CH = 2 * NP;
+  __shared__ float red[kSegs][32][5 * CH + 1];
+  const int d0 = (blockIdx.x * 32 + threadIdx.x) * CH;
   const int b = blockIdx.z;
   const int t0 = (blockIdx.y * kSegs + threadIdx.y) * tl;
   const bool active = d0 < a.D && t0 < a.L;
   const float2 zero2 = make_float2(0.f, 0.f);
-  float2 dwa[4][2], dba[2];   // [tap][channel pair]
+  float2 dwa[4][NP], dba[NP];   // [tap][channel pair]
 #pragma unroll
-  for (int pr = 0; pr < 2; ++pr) {
+  for (int pr = 0; pr < NP; ++pr) {
     dba[pr] = zero2;
 #pragma unroll
     for (int k = 0; k < 4; ++k) dwa[k][pr] = zero2;
   }
   if (active) {
-    float2 w[4][2], bia[2];
+    float2 w[4][NP], bia[NP];
 #pragma unroll
-    for (int pr = 0; pr < 2; ++pr) {
+    for (int pr = 0; pr < NP; ++pr) {
       const int64_t da = d0 + 2 * pr, db = d0 + 2 * pr + 1;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -499,23 +518,23 @@ __global__ void __launch_bounds__(32 * kSegs, 4) conv1d_bwd_fast_kernel(ConvArgs
     const T* __restrict__ gp = gbase + b * a.gs_b + d0;
     T* __restrict__ dxp = dxbase + b * a.ds_b + d0;
     const int xsl = (int)a.xs_l, gsl = (int)a.gs_l, dsl = (int)a.ds_l;   // (row pitches fit 32 bits: checked by the host)
-    const uint2 z2 = make_uint2(0u, 0u);
-    float2 p1[2], p2[2], p3[2];     // x[t-1], x[t-2], x[t-3]
-    float2 g1[2], g2[2], g3[2];     // dc[t-1], dc[t-2], dc[t-3]
-    unpack22<T>(t0 >= 1 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 1) * xsl)) : z2, p1);
-    unpack22<T>(t0 >= 2 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 2) * xsl)) : z2, p2);
-    unpack22<T>(t0 >= 3 ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)(t0 - 3) * xsl)) : z2, p3);
+    const Raw z2 = raw_zero<NP>();
+    float2 p1[NP], p2[NP], p3[NP];     // x[t-1], x[t-2], x[t-3]
+    float2 g1[NP], g2[NP], g3[NP];     // dc[t-1], dc[t-2], dc[t-3]
+    unpack_np<T, NP>(t0 >= 1 ? __ldg(reinterpret_cast<const Raw*>(xp + (int64_t)(t0 - 1) * xsl)) : z2, p1);
+    unpack_np<T, NP>(t0 >= 2 ? __ldg(reinterpret_cast<const Raw*>(xp + (int64_t)(t0 - 2) * xsl)) : z2, p2);
+    unpack_np<T, NP>(t0 >= 3 ? __ldg(reinterpret_cast<const Raw*>(xp + (int64_t)(t0 - 3) * xsl)) : z2, p3);
 #pragma unroll
-    for (int pr = 0; pr < 2; ++pr) g1[pr] = g2[pr] = g3[pr] = zero2;
+    for (int pr = 0; pr < NP; ++pr) g1[pr] = g2[pr] = g3[pr] = zero2;
     const int own_end = min(t0 + tl, a.L);
     const int tlast = own_end + 3;   // exclusive; dc beyond L is zero
     // one token: `own` = its dc feeds this thread's dweight / dbias sums, `store` = dx[t - 3] is a row of this thread
-    auto token = [&](uint2 rx, uint2 rg, bool own, bool store, T* dst) {
-      float2 c[2], g[2], r[2];
-      unpack22<T>(rx, c);
-      unpack22<T>(rg, g);
+    auto token = [&](Raw rx, Raw rg, bool own, bool store, T* dst) {
+      float2 c[NP], g[NP], r[NP];
+      unpack_np<T, NP>(rx, c);
+      unpack_np<T, NP>(rg, g);
 #pragma unroll
-      for (int pr = 0; pr < 2; ++pr) {
+      for (int pr = 0; pr < NP; ++pr) {
         if (SILU) {
           const float2 pre = fma2p(w[3][pr], c[pr], fma2p(w[2][pr], p1[pr], fma2p(w[1][pr], p2[pr], fma2p(w[0][pr], p3[pr], bia[pr]))));
           g[pr] = mul2p(g[pr], dsilu2(pre));
@@ -531,12 +550,12 @@ __global__ void __launch_bounds__(32 * kSegs, 4) conv1d_bwd_fast_kernel(ConvArgs
         p3[pr] = p2[pr]; p2[pr] = p1[pr]; p1[pr] = c[pr];
         g3[pr] = g2[pr]; g2[pr] = g1[pr]; g1[pr] = g[pr];
       }
-      if (store) *reinterpret_cast<uint2*>(dst) = pack22<T>(r);
+      if (store) *reinterpret_cast<Raw*>(dst) = pack_np<T, NP>(r);
     };
     auto edge_token = [&](int t) {   // any token of [t0, tlast): loads guarded by L, flags from its position
       const bool in = t < a.L;
-      token(in ? __ldg(reinterpret_cast<const uint2*>(xp + (int64_t)t * xsl)) : z2,
-            in ? __ldg(reinterpret_cast<const uint2*>(gp + (int64_t)t * gsl)) : z2, t < own_end, t - 3 >= t0,
+      token(in ? __ldg(reinterpret_cast<const Raw*>(xp + (int64_t)t * xsl)) : z2,
+            in ? __ldg(reinterpret_cast<const Raw*>(gp + (int64_t)t * gsl)) : z2, t < own_end, t - 3 >= t0,
             dxp + (int64_t)(t - 3) * dsl);
     };
     int t = t0;
@@ -547,14 +566,14 @@ __global__ void __launch_bounds__(32 * kSegs, 4) conv1d_bwd_fast_kernel(ConvArgs
     // (ptxas places loads that nothing in the body consumes at its end whatever the source order - half-batch rotation with a
     // __syncwarp as a scheduling fence was measured 25 % slower, more registers at 12 warps per SM 5 % slower).
     if (t + kCB <= own_end) {
-      uint2 rx[kCB], rg[kCB];
+      Raw rx[kCB], rg[kCB];
       {
         const T* px = xp + (int64_t)t * xsl;
         const T* pg = gp + (int64_t)t * gsl;
 #pragma unroll
         for (int u = 0; u < kCB; ++u) {
-          rx[u] = __ldg(reinterpret_cast<const uint2*>(px + u * xsl));
-          rg[u] = __ldg(reinterpret_cast<const uint2*>(pg + u * gsl));
+          rx[u] = __ldg(reinterpret_cast<const Raw*>(px + u * xsl));
+          rg[u] = __ldg(reinterpret_cast<const Raw*>(pg + u * gsl));
         }
       }
 #pragma unroll 1
@@ -565,8 +584,8 @@ __global__ void __launch_bounds__(32 * kSegs, 4) conv1d_bwd_fast_kernel(ConvArgs
 #pragma unroll
         for (int u = 0; u < kCB; ++u) {
           token(rx[u], rg[u], true, true, pd + u * dsl);
-          rx[u] = __ldg(reinterpret_cast<const uint2*>(px + u * xsl));
-          rg[u] = __ldg(reinterpret_cast<const uint2*>(pg + u * gsl));
+          rx[u] = __ldg(reinterpret_cast<const Raw*>(px + u * xsl));
+          rg[u] = __ldg(reinterpret_cast<const Raw*>(pg + u * gsl));
         }
       }
       {   // the last full batch
@@ -582,7 +601,7 @@ __global__ void __launch_bounds__(32 * kSegs, 4) conv1d_bwd_fast_kernel(ConvArgs
   }
   // reduce dweight / dbias over the block's token segments, then one atomic per (channel, tap)
 #pragma unroll
-  for (int pr = 0; pr < 2; ++pr) {
+  for (int pr = 0; pr < NP; ++pr) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       red[threadIdx.y][threadIdx.x][(2 * pr) * 5 + k] = dwa[k][pr].x;
@@ -594,7 +613,7 @@ __global__ void __launch_bounds__(32 * kSegs, 4) conv1d_bwd_fast_kernel(ConvArgs
   __syncthreads();
   if (threadIdx.y == 0 && d0 < a.D) {
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
+    for (int v = 0; v < CH; ++v) {
 #pragma unroll
       for (int k = 0; k <= 4; ++k) {
         float sum = 0.f;
@@ -629,12 +648,23 @@ bool try_launch_bwd_fast(const ConvArgs& a, int W, const omni_tensor_t& x, const
       const int nblk = (a.L + kSegs * 64 - 1) / (kSegs * 64);
       tl = (a.L + kSegs * nblk - 1) / (kSegs * nblk);
     }
-    dim3 block(32, kSegs), grid((unsigned)cols, (a.L + kSegs * tl - 1) / (kSegs * tl), a.B);
+#ifndef OMNI_CONV_BWD_NP
+#define OMNI_CONV_BWD_NP 2
+#endif
+#ifndef OMNI_CONV_BWD_CB
+#define OMNI_CONV_BWD_CB 8
+#endif
+#ifndef OMNI_CONV_BWD_MINB
+#define OMNI_CONV_BWD_MINB 4
+#endif
+    constexpr int NP = OMNI_CONV_BWD_NP, CB = OMNI_CONV_BWD_CB, MINB = OMNI_CONV_BWD_MINB;
+    const int64_t colsn = (a.D + 64 * NP - 1) / (64 * NP);
+    dim3 block(32, kSegs), grid((unsigned)colsn, (a.L + kSegs * tl - 1) / (kSegs * tl), a.B);
     const T* xb = static_cast<const T*>(a.x);
     const T* gb = static_cast<const T*>(a.dout);
     T* db = static_cast<T*>(a.dx);
-    if (a.silu) conv1d_bwd_fast_kernel<T, true><<<grid, block, 0, s>>>(a, tl, xb, gb, db);
-    else conv1d_bwd_fast_kernel<T, false><<<grid, block, 0, s>>>(a, tl, xb, gb, db);
+    if (a.silu) conv1d_bwd_fast_kernel<T, true, NP, CB, MINB><<<grid, block, 0, s>>>(a, tl, xb, gb, db);
+    else conv1d_bwd_fast_kernel<T, false, NP, CB, MINB><<<grid, block, 0, s>>>(a, tl, xb, gb, db);
     return true;
   }
 }

@@ -3,7 +3,7 @@
 tag=$1; shift
 mkdir -p gpurun_out
 {
-for round in 1 2; do
+for round in ${ROUNDS:-1 2}; do
   for name in "$@"; do
     if [ "$name" = "cur" ]; then unset OMNI_LIB_PATH; else export OMNI_LIB_PATH=$PWD/.ab/lib_$name.so; fi
     echo "== $name (round $round)"
