@@ -284,8 +284,9 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     if (++it.c == it.cend) it_set(it, it.u + 1);
   };
   // (one instantiation per mode: the forward does not carry the sweeps' code and vice versa.)  MODE 3 = the forward of a caller
-  // that will run the backward: as mode 0, plus the TMA store of the fp16 state entering every chunk (the S16 tile the state
-  // keepers build for Yoff anyway) - what the backward's forward sweep (mode 1) would otherwise recompute.
+  // that will run the backward: as mode 0, plus a copy of the fp16 state entering every chunk (the S16 tile the state
+  // keepers build for Yoff anyway, each warp TMA-storing its own rows) - what the backward's forward sweep (mode 1) would
+  // otherwise recompute.
   constexpr int mode = MODE == 3 ? 0 : MODE;
   constexpr bool save = MODE == 3;
   constexpr int leadE = mode == 0 ? kLeadEFwd : kLeadE;
@@ -815,6 +816,8 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     ChunkIter sn, ep;  // chunk gg (state step) and chunk gg - 1 (epilogue)
     it_set(sn, 0);
     ep = sn;
+    bool keep_pending = false;   // MODE 3: a chunk-state store of this warp may still be reading its rows of the S16 tile
+    int epi_groups = 0;          // y-store groups this warp committed in the last epilogue (4 or 0)
     int pend = 0, pend_b = 0, pend_h0 = 0;  // unit that ended with the previous state step: 1 = whole item / second half, 2 = first half
     // state at the end of a unit (all of TM_S, complete once the unit's last S-update has been waited for): the final state
     // of the item, or - first half of a split item - the hand-off slot of this CTA followed by its flag
@@ -860,6 +863,7 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         if (w == 0) TR(19);
         const int eb = ep.b, eh0 = ep.h0, ec = ep.c;
         const int t = ec * Q + r;
+        epi_groups = (!kDirectY && a.out_dtype == OMNI_BF16 && ec * Q + w * 32 < a.L) ? 4 : 0;
 #pragma unroll 1
         for (int s4 = 0; s4 < 4; ++s4) {  // s4 = head * 2 + 32-column half
           const int hx = s4 >> 1, half = s4 & 1;
@@ -943,16 +947,18 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         named_bar_sync(6, 128);
         const float dch = tab->dchunk[hh];
-        if (mode != 0 || save) {  // state stores: the previous TMA store must have read the S16 tile
-          // (forward with stores: warp 0's lane 0 also commits that warp's y stores - `elect_one` picks lane 0.  With bf16 output
-          // exactly four y groups - the epilogue of chunk gg - 1, always in range for warp 0 - were committed after the state
-          // store of step gg - 1: those may stay pending.  Measured: the forward with stores is 12 % slower than the plain one
-          // either way - the cost is the 32 KB read of the S16 tile beside the MMA's own reads, not this wait)
-          if (w == 0 && lane == 0) {
-            if (save && !kDirectY && a.out_dtype == OMNI_BF16) tma_store_wait_read<4>();
-            else tma_store_wait_read<0>();
-          }
+        if (mode != 0) {  // state sweeps: the previous TMA store must have read the S16 tile
+          if (w == 0 && lane == 0) tma_store_wait_read<0>();
           named_bar_sync(1, 128);
+        }
+        if (save && keep_pending) {
+          // this warp's store of the previous step must have read its rows of the tile.  The groups committed since are the y
+          // stores of the epilogue just finished: exactly four with bf16 output when the warp's rows are inside the sequence
+          // (those may stay pending), none otherwise
+          if (lane == 0) {
+            if (epi_groups == 4) tma_store_wait_read<4>(); else tma_store_wait_read<0>();
+          }
+          __syncwarp();
         }
         if (gg > 0) tc_fence_after();
         if (w == 0) TR(15);
@@ -1044,7 +1050,21 @@ ssd_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         __syncwarp();
         if (w == 0) TR(16);
         if (lane == 0) mbar_arrive(&bars[B_S_READY]);
-        if ((mode != 0 && !a.no_store) || save) {  // the state ENTERING this chunk -> workspace[b][chunk][(h,p)][n] (fp16)
+        if (save) {
+          // Forward that keeps its chunk states: every warp stores ITS OWN 32 rows of the tile (each thread wrote row r, both
+          // n-halves) with two 4 KB TMA stores - no barrier between the four warps, which otherwise run their state step and
+          // epilogue independently.  Measured at (16, 4096), plain forward 0.385 ms: this form 0.438 ms, one 32 KB store by one
+          // thread behind two 128-thread barriers 0.430 ms, a coalesced LSU copy by the four warps 0.450 ms - the ~12 % are
+          // the price of the extra 0.54 GB written beside the stream (+49 % DRAM traffic), not of how the tile leaves.
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&mapS, smem + SM_S + w * 4096, 0, sn.h0 * HD + w * 32, sn.c, sn.b);
+            tma_store_4d(&mapS, smem + SM_S + 16384 + w * 4096, 64, sn.h0 * HD + w * 32, sn.c, sn.b);
+            tma_store_commit();
+          }
+          keep_pending = true;
+        }
+        if (mode != 0 && !a.no_store) {  // state sweeps: the state ENTERING this chunk -> workspace[b][chunk][(h,p)][n] (fp16)
           named_bar_sync(1, 128);
           if (w == 0 && lane == 0) {
             tma_store_4d(&mapS, smem + SM_S, 0, sn.h0 * HD, cphys(sn.c), sn.b);
@@ -1324,10 +1344,10 @@ int tc_launch(int mode, const omni_tensor_t& x, const omni_tensor_t& dt, const o
     mY = mX;  // unused
   }
   const bool save = mode == 0 && ws_states != nullptr;   // forward that also stores the chunk states (kernel MODE 3)
-  if ((mode != 0 && !no_store) || save) {  // fp16 states: (n 128, rows H*64, chunk, batch), box 64 x 128 rows
+  if ((mode != 0 && !no_store) || save) {  // fp16 states: (n 128, rows H*64, chunk, batch), box 64 x 128 rows (MODE 3: 32 rows)
     const uint64_t dims[4] = {(uint64_t)NS, (uint64_t)(H * HD), (uint64_t)nchunks, (uint64_t)Bsz};
     const uint64_t strides[3] = {(uint64_t)NS * 2, (uint64_t)(H * HD * NS) * 2, (uint64_t)(nchunks * H * HD * NS) * 2};
-    const uint32_t box[4] = {64, 128, 1, 1};
+    const uint32_t box[4] = {64, save ? 32u : 128u, 1, 1};
     if (int rc = make_tmap_16bit(&mS, ws_states, 4, dims, strides, box, false)) return rc;
   } else {
     mS = mX;  // unused
